@@ -1,0 +1,67 @@
+"""ctypes binding of libgeo4d_b200.so (the C-ABI product boundary, include/geo4d_b200.h).
+
+There is deliberately NO fallback: if the library is missing, fails to load, or
+the device is not a Blackwell part, every op raises.  The CPU oracle lives in
+``oracle/`` and is never reachable from here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgeo4d_b200.so")
+
+
+class Geo4DError(RuntimeError):
+    pass
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("K", C.c_int), ("W", C.c_int), ("H", C.c_int), ("N", C.c_int),
+        ("a_stride_w", C.c_int64), ("a_stride_h", C.c_int64), ("a_stride_n", C.c_int64),
+        ("box_w", C.c_int), ("box_h", C.c_int), ("box_n", C.c_int),
+        ("num_taps", C.c_int), ("tap_dx", C.c_int * 9), ("tap_dy", C.c_int * 9),
+        ("b", C.c_void_p), ("n_out", C.c_int), ("b_batched", C.c_int),
+        ("out", C.c_void_p), ("ldc", C.c_int64), ("out_fp32", C.c_int), ("alpha", C.c_float),
+        ("bias", C.c_void_p), ("row_bias", C.c_void_p), ("row_bias_ld", C.c_int64),
+        ("rows_per_bias", C.c_int), ("act", C.c_int),
+        ("residual", C.c_void_p), ("ldr", C.c_int64),
+    ]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the library (once).  Raises Geo4DError if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Geo4DError(
+                f"{LIB_PATH} not found: build it with `python -m geo4d_b200.build` "
+                "(there is no CPU/PyTorch fallback for the product path)")
+        try:
+            _lib = C.CDLL(LIB_PATH)
+        except OSError as e:  # pragma: no cover
+            raise Geo4DError(f"cannot load {LIB_PATH}: {e}") from e
+        _lib.geo4d_last_error.restype = C.c_char_p
+        _lib.geo4d_abi_version.restype = C.c_int
+    return _lib
+
+
+def check(rc: int, what: str = "geo4d"):
+    if rc != 0:
+        msg = lib().geo4d_last_error().decode(errors="replace")
+        raise Geo4DError(f"{what} failed (code {rc}): {msg}")
+
+
+def require_device():
+    import torch
+    if not torch.cuda.is_available():
+        raise Geo4DError("geo4d_b200 needs a CUDA device (B200, sm_100a); none is visible and "
+                         "there is no CPU fallback")
+    if not lib().geo4d_device_supported():
+        raise Geo4DError("geo4d_b200 kernels are compiled for sm_100a only; current device is not "
+                         "compute capability 10.x")

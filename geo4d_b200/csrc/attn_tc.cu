@@ -1,0 +1,317 @@
+// Fused softmax attention on tcgen05 tensor cores (head dim 64, non-causal), the "one true dense
+// contraction" of the U-Net: replaces xformers.ops.memory_efficient_attention as called by
+// CrossAttention.efficient_forward (attention.py:146-209) for spatial self-attention and for the two
+// cross-attention branches (text keys, per-frame image keys; the second branch is summed into the first
+// with `accumulate`, attention.py:203-207).  QK-scale, softmax and PV are fused; scores never leave the SM.
+//
+//  grid : one CTA per (batch, head, 128-query tile); two CTAs co-reside per SM (112 KB smem, 256 TMEM
+//         columns each) so one CTA's softmax overlaps the other's MMAs.
+//  warp 0 lane 0 : TMA producer  (Q once; K_j, V_j double buffered; 4-D maps read heads in place from the
+//                  token-major [rows, heads*64] projections -- no head-split copies)
+//  warp 1 lane 0 : tcgen05.mma   S = Q K_j^T  (M128 N128 K64, both K-major)        -> TMEM cols [0,128)
+//                                O += P_j V_j (M128 N64 K128, P from smem K-major,
+//                                              V MN-major straight from its TMA tile) -> TMEM cols [128,192)
+//  warps 2..5    : one query row per thread: tcgen05.ld S, running max / sum in fp32, exp2 with the
+//                  1/sqrt(d)*log2(e) scale folded in, rescale O in TMEM only when the max moved,
+//                  write P (bf16, 128B-swizzled) to smem, final O / l -> bf16 store.
+#include "common.cuh"
+#include "geo4d_b200.h"
+
+namespace g4 {
+
+struct AttnArgs {
+  int B, H, Lq, Lk;
+  int n_qtiles, n_kvtiles;
+  int kv_shared;
+  int accumulate;
+  float scale_log2;  // scale * log2(e)
+  void* out;
+  long long ldo;
+};
+
+constexpr int AT_Q_BYTES = 128 * 64 * 2;   // 16 KB
+constexpr int AT_KV_BYTES = 128 * 64 * 2;  // 16 KB per K or V tile
+constexpr int AT_P_BYTES = 128 * 128 * 2;  // 32 KB
+constexpr int AT_SMEM = AT_Q_BYTES + 4 * AT_KV_BYTES + AT_P_BYTES;  // 112 KB
+
+__global__ void __launch_bounds__(192, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnArgs args) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bars[12];
+  __shared__ uint32_t tmem_slot;
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + AT_Q_BYTES;                    // [2]
+  uint8_t* sV = smem + AT_Q_BYTES + 2 * AT_KV_BYTES;  // [2]
+  uint8_t* sP = smem + AT_Q_BYTES + 4 * AT_KV_BYTES;
+  uint64_t* q_full = &bars[0];
+  uint64_t* k_full = &bars[1];   // [2]
+  uint64_t* k_empty = &bars[3];  // [2]
+  uint64_t* v_full = &bars[5];   // [2]
+  uint64_t* v_empty = &bars[7];  // [2]
+  uint64_t* s_full = &bars[9];
+  uint64_t* p_ready = &bars[10];
+  uint64_t* pv_done = &bars[11];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x % args.n_qtiles;
+  const int bh = blockIdx.x / args.n_qtiles;
+  const int h = bh % args.H;
+  const int b = bh / args.H;
+  const int bkv = args.kv_shared ? 0 : b;
+  const int nkv = args.n_kvtiles;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 128);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const uint32_t tS = tmem_base;        // 128 columns
+  const uint32_t tO = tmem_base + 128;  // 64 columns
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, AT_Q_BYTES);
+      tma_load_4d(sQ, &tmQ, q_full, 0, h, qt * 128, b);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_expect_tx(&k_full[st], AT_KV_BYTES);
+        tma_load_4d(sK + st * AT_KV_BYTES, &tmK, &k_full[st], 0, h, j * 128, bkv);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_expect_tx(&v_full[st], AT_KV_BYTES);
+        tma_load_4d(sV + st * AT_KV_BYTES, &tmV, &v_full[st], 0, h, j * 128, bkv);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);  // B (= V) is MN-major
+      const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        const uint32_t aK = smem_u32(sK + st * AT_KV_BYTES);
+        const uint32_t aV = smem_u32(sV + st * AT_KV_BYTES);
+        // S_j = Q K_j^T  (S is free: the softmax warps finished reading S_{j-1} before p_ready(j-1))
+        mbar_wait(&k_full[st], ph);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_ss(tS, make_sw128_desc(aQ + kk * 32, 16, 1024), make_sw128_desc(aK + kk * 32, 16, 1024), idesc_qk,
+                  kk != 0);
+        umma_commit(&k_empty[st]);
+        umma_commit(s_full);
+        // O += P_j V_j
+        mbar_wait(&v_full[st], ph);
+        mbar_wait(p_ready, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_ss(tO, make_sw128_desc(aP + kb * 16384 + kk * 32, 16, 1024),
+                    make_sw128_desc(aV + kb * 8192 + kk * 2048, 1024, 1024), idesc_pv, (j | kb | kk) != 0);
+        umma_commit(&v_empty[st]);
+        umma_commit(pv_done);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;  // query row within the tile == TMEM lane
+    const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+    const float sl2 = args.scale_log2;
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      const int kv_valid = min(128, args.Lk - j * 128);  // keys of this tile that exist
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      // pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tS + lane_off + c * 32, v);
+        tmem_ld_wait();
+        if (kv_valid >= (c + 1) * 32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+      }
+      const float m_new = fmaxf(m, mx);
+      const float alpha = (m == -INFINITY) ? 0.f : exp2f((m - m_new) * sl2);
+      const float mb = m_new * sl2;
+      // the previous PV must have retired before O is rescaled / P is overwritten
+      mbar_wait(pv_done, (j & 1) ^ 1);
+      tc_fence_after();
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tO + lane_off + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          tmem_st32(tO + lane_off + c * 32, v);
+        }
+        tmem_st_wait();
+      }
+      // pass 2: p = exp2(s*sl2 - m*sl2), row sum, bf16 P tile (K-major, 128B swizzle) to smem
+      float rs = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tS + lane_off + c * 32, v);
+        tmem_ld_wait();
+        float p[32];
+        if (kv_valid >= (c + 1) * 32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) p[i] = exp2f(fmaf(__uint_as_float(v[i]), sl2, -mb));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            p[i] = (c * 32 + i < kv_valid) ? exp2f(fmaf(__uint_as_float(v[i]), sl2, -mb)) : 0.f;
+        }
+        uint8_t* prow = sP + (c >> 1) * 16384 + r * 128;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          uint4 w;
+          w.x = pack_bf16x2(p[8 * qq + 0], p[8 * qq + 1]);
+          w.y = pack_bf16x2(p[8 * qq + 2], p[8 * qq + 3]);
+          w.z = pack_bf16x2(p[8 * qq + 4], p[8 * qq + 5]);
+          w.w = pack_bf16x2(p[8 * qq + 6], p[8 * qq + 7]);
+          // row sum over the bf16-rounded probabilities (what the PV MMA actually sums)
+          float2 f;
+          f = unpack_bf16x2(w.x); rs += f.x + f.y;
+          f = unpack_bf16x2(w.y); rs += f.x + f.y;
+          f = unpack_bf16x2(w.z); rs += f.x + f.y;
+          f = unpack_bf16x2(w.w); rs += f.x + f.y;
+          const int chunk = ((c & 1) * 4 + qq) ^ (r & 7);
+          *reinterpret_cast<uint4*>(prow + chunk * 16) = w;
+        }
+      }
+      l = l * alpha + rs;
+      m = m_new;
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(p_ready);
+    }
+    // epilogue: O / l -> bf16
+    mbar_wait(pv_done, (nkv - 1) & 1);
+    tc_fence_after();
+    const int lq = qt * 128 + r;
+    const float inv_l = 1.0f / l;
+    __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(args.out) + ((long long)b * args.Lq + lq) * args.ldo + h * 64;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tO + lane_off + c * 32, v);
+      tmem_ld_wait();
+      if (lq < args.Lq) {
+        uint4* o4 = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          float o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[8 * qq + i]) * inv_l;
+          if (args.accumulate) {
+            const uint4 pr = o4[qq];
+            float2 f;
+            f = unpack_bf16x2(pr.x); o[0] += f.x; o[1] += f.y;
+            f = unpack_bf16x2(pr.y); o[2] += f.x; o[3] += f.y;
+            f = unpack_bf16x2(pr.z); o[4] += f.x; o[5] += f.y;
+            f = unpack_bf16x2(pr.w); o[6] += f.x; o[7] += f.y;
+          }
+          uint4 w;
+          w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
+          w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
+          o4[qq] = w;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+}  // namespace g4
+
+using namespace g4;
+
+extern "C" int geo4d_attention(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* out,
+                               int64_t ldo, int B, int H, int Lq, int Lk, int kv_shared, int accumulate, float scale,
+                               g4_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!q || !k || !v || !out) { set_last_error("attention: null pointer"); return G4_ERR_BAD_ARG; }
+  if (B < 1 || H < 1 || Lq < 1 || Lk < 1) { set_last_error("attention: bad sizes B=%d H=%d Lq=%d Lk=%d", B, H, Lq, Lk); return G4_ERR_BAD_ARG; }
+  if (ldq % 8 || ldkv % 8 || ldo % 8 || ((uintptr_t)q & 15) || ((uintptr_t)k & 15) || ((uintptr_t)v & 15) ||
+      ((uintptr_t)out & 15)) {
+    set_last_error("attention: pointers must be 16-byte aligned and leading dims multiples of 8"); return G4_ERR_BAD_ARG;
+  }
+  CUtensorMap tmQ, tmK, tmV;
+  {
+    uint64_t dims[4] = {64, (uint64_t)H, (uint64_t)Lq, (uint64_t)B};
+    uint64_t str[3] = {128, (uint64_t)ldq * 2, (uint64_t)ldq * 2 * (uint64_t)Lq};
+    uint32_t box[4] = {64, 1, 128, 1};
+    int rc = make_tmap_bf16(&tmQ, q, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {64, (uint64_t)H, (uint64_t)Lk, (uint64_t)(kv_shared ? 1 : B)};
+    uint64_t str[3] = {128, (uint64_t)ldkv * 2, (uint64_t)ldkv * 2 * (uint64_t)Lk};
+    uint32_t box[4] = {64, 1, 128, 1};
+    int rc = make_tmap_bf16(&tmK, k, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tmV, v, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  AttnArgs a;
+  a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk;
+  a.n_qtiles = (Lq + 127) / 128;
+  a.n_kvtiles = (Lk + 127) / 128;
+  a.kv_shared = kv_shared; a.accumulate = accumulate;
+  a.scale_log2 = scale * 1.4426950408889634f;
+  a.out = out; a.ldo = ldo;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    if (e != cudaSuccess) { set_last_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return G4_ERR_CUDA; }
+    attr_set = true;
+  }
+  const long long grid = (long long)a.n_qtiles * B * H;
+  if (grid > 2147483647ll) { set_last_error("attention: grid too large"); return G4_ERR_UNSUPPORTED; }
+  attn_fwd_kernel<<<(int)grid, 192, AT_SMEM, stream>>>(tmQ, tmK, tmV, a);
+  return check_launch("attention");
+}

@@ -1,0 +1,271 @@
+"""Thin Python wrappers over the C-ABI kernels (device tensors in, device tensors out).
+
+Activation layout everywhere: bf16, frames-major channels-last, i.e. a feature
+map of N frames is a 2-D matrix [N*H*W, C] (row = ((n*H)+y)*W+x).  All wrappers
+enqueue on torch's current stream and never synchronise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from functools import lru_cache
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _cabi
+from ._cabi import GemmDesc, check, lib
+
+ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
+
+TAPS_1 = ((0, 0),)
+TAPS_3x3 = tuple((dx, dy) for dy in (-1, 0, 1) for dx in (-1, 0, 1))  # weight[:, :, ky, kx] order
+TAPS_T3 = ((0, -1), (0, 0), (0, 1))  # temporal taps act on the H (= frame) axis
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+@lru_cache(maxsize=None)
+def pick_box(W: int, H: int, N: int) -> Tuple[int, int, int]:
+    """Choose the (box_w, box_h, box_n) M-tile (<=128 rows) wasting the fewest MMA rows."""
+    best, best_key = None, None
+    bws = sorted({d for d in range(1, min(W, 128) + 1) if W % d == 0} | ({128} if W > 128 else set()))
+    for bw in bws:
+        for bh in range(1, min(H, 128 // bw) + 1):
+            for bn in range(1, min(N, 128 // (bw * bh)) + 1):
+                tiles = -(-W // bw) * -(-H // bh) * -(-N // bn)
+                eff = (W * H * N) / (tiles * 128.0)
+                key = (round(eff, 6), bw * bh * bn, bw, bh)
+                if best_key is None or key > best_key:
+                    best, best_key = (bw, bh, bn), key
+    return best
+
+
+def tap_gemm(a: torch.Tensor, K: int, W: int, H: int, N: int, strides: Tuple[int, int, int],
+             taps: Sequence[Tuple[int, int]], b: torch.Tensor, n_out: int, out: torch.Tensor, ldc: int,
+             *, bias: Optional[torch.Tensor] = None, row_bias: Optional[torch.Tensor] = None,
+             rows_per_bias: int = 0, act: int = ACT_NONE, residual: Optional[torch.Tensor] = None,
+             ldr: int = 0, alpha: float = 1.0, b_batched: bool = False,
+             box: Optional[Tuple[int, int, int]] = None) -> torch.Tensor:
+    d = GemmDesc()
+    d.a = a.data_ptr()
+    d.K, d.W, d.H, d.N = K, W, H, N
+    d.a_stride_w, d.a_stride_h, d.a_stride_n = strides
+    bw, bh, bn = box if box is not None else pick_box(W, H, 1 if b_batched else N)
+    d.box_w, d.box_h, d.box_n = bw, bh, bn
+    d.num_taps = len(taps)
+    for i, (dx, dy) in enumerate(taps):
+        d.tap_dx[i] = dx
+        d.tap_dy[i] = dy
+    d.b = b.data_ptr()
+    d.n_out = n_out
+    d.b_batched = 1 if b_batched else 0
+    d.out = out.data_ptr()
+    d.ldc = ldc
+    d.out_fp32 = 1 if out.dtype == torch.float32 else 0
+    d.alpha = alpha
+    d.bias = _ptr(bias)
+    d.row_bias = _ptr(row_bias)
+    d.row_bias_ld = row_bias.stride(0) if row_bias is not None else 0
+    d.rows_per_bias = rows_per_bias
+    d.act = act
+    d.residual = _ptr(residual)
+    d.ldr = ldr
+    check(lib().geo4d_tap_gemm(C.byref(d), C.c_void_p(_stream())), "geo4d_tap_gemm")
+    return out
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
+           out: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+           residual: Optional[torch.Tensor] = None, alpha: float = 1.0,
+           out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """out[M, n] = epilogue(x[M, K] @ w[n, K]^T).  x may be a row-strided view."""
+    assert x.dim() == 2 and w.dim() == 2 and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    M, K = x.shape
+    n = w.shape[0]
+    n_store = n // 2 if act == ACT_GEGLU else n
+    if out is None:
+        out = torch.empty((M, n_store), device=x.device, dtype=out_dtype)
+    ldr = residual.stride(0) if residual is not None else 0
+    lda = x.stride(0)
+    return tap_gemm(x, K, M, 1, 1, (lda, lda * M, lda * M), TAPS_1, w, n, out, out.stride(0),
+                    bias=bias, act=act, residual=residual, ldr=ldr, alpha=alpha)
+
+
+def conv3x3(x: torch.Tensor, N: int, H: int, W: int, w9: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
+            out: Optional[torch.Tensor] = None, row_bias: Optional[torch.Tensor] = None,
+            rows_per_bias: int = 0, residual: Optional[torch.Tensor] = None,
+            out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """3x3, stride 1, zero pad 1.  x [N*H*W, Cin] bf16; w9 [9, Cout, Cin] bf16 (tap = ky*3+kx)."""
+    Cin = x.shape[1]
+    Cout = w9.shape[1]
+    if out is None:
+        out = torch.empty((N * H * W, Cout), device=x.device, dtype=out_dtype)
+    ld = x.stride(0)
+    ldr = residual.stride(0) if residual is not None else 0
+    return tap_gemm(x, Cin, W, H, N, (ld, ld * W, ld * W * H), TAPS_3x3, w9, Cout, out, out.stride(0),
+                    bias=bias, row_bias=row_bias, rows_per_bias=rows_per_bias, residual=residual, ldr=ldr)
+
+
+def temporal_conv3(x: torch.Tensor, B: int, T: int, HW: int, w3: torch.Tensor,
+                   bias: Optional[torch.Tensor] = None, *, out: Optional[torch.Tensor] = None,
+                   residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Conv3d kernel (3,1,1), pad (1,0,0).  x [(B*T*HW), C] bf16; w3 [3, Cout, Cin]."""
+    Cin = x.shape[1]
+    Cout = w3.shape[1]
+    if out is None:
+        out = torch.empty((B * T * HW, Cout), device=x.device, dtype=torch.bfloat16)
+    ld = x.stride(0)
+    ldr = residual.stride(0) if residual is not None else 0
+    return tap_gemm(x, Cin, HW, T, B, (ld, ld * HW, ld * HW * T), TAPS_T3, w3, Cout, out, out.stride(0),
+                    bias=bias, residual=residual, ldr=ldr)
+
+
+def bmm_nt(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = None, alpha: float = 1.0,
+           out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """out[i] = alpha * a[i] @ b[i]^T with a [B, M, K], b [B, n, K] (both K-contiguous)."""
+    Bt, M, K = a.shape
+    n = b.shape[1]
+    if out is None:
+        out = torch.empty((Bt, M, n), device=a.device, dtype=out_dtype)
+    return tap_gemm(a, K, M, 1, Bt, (a.stride(1), a.stride(1) * M, a.stride(0)), TAPS_1, b, n, out, out.stride(1),
+                    alpha=alpha, b_batched=True, box=(min(M, 128), 1, 1))
+
+
+# --------------------------------------------------------------------------- other kernels
+def _vp(t):
+    return C.c_void_p(None if t is None else t.data_ptr())
+
+
+def _s():
+    return C.c_void_p(_stream())
+
+
+_gn_ws = {}
+
+
+def _gn_workspace(device, num_stats: int) -> torch.Tensor:
+    need = num_stats * 64
+    ws = _gn_ws.get(device)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 64 * 64), device=device, dtype=torch.float32)
+        _gn_ws[device] = ws
+    return ws
+
+
+def groupnorm(x: torch.Tensor, num_stats: int, rows_per_stat: int, gamma: torch.Tensor, beta: torch.Tensor,
+              eps: float, silu: bool, out: Optional[torch.Tensor] = None,
+              workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GroupNorm(32 groups)[+SiLU] on rows [num_stats*rows_per_stat, C] bf16; fp32 affine."""
+    Cc = x.shape[1]
+    if out is None:
+        out = torch.empty((x.shape[0], Cc), device=x.device, dtype=torch.bfloat16)
+    ws = workspace if workspace is not None else _gn_workspace(x.device, num_stats)
+    check(lib().geo4d_groupnorm_silu(_vp(x), C.c_int64(x.stride(0)), _vp(out), C.c_int64(out.stride(0)),
+                                     num_stats, rows_per_stat, Cc, _vp(gamma), _vp(beta), C.c_float(eps),
+                                     1 if silu else 0, _vp(ws), C.c_size_t(ws.numel() * 4), _s()),
+          "geo4d_groupnorm_silu")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    M, Cc = x.shape
+    if out is None:
+        out = torch.empty((M, Cc), device=x.device, dtype=torch.bfloat16)
+    check(lib().geo4d_layernorm(_vp(x), C.c_int64(x.stride(0)), _vp(out), C.c_int64(out.stride(0)), M, Cc,
+                                _vp(gamma), _vp(beta), C.c_float(eps), _s()), "geo4d_layernorm")
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, B: int, H: int, Lq: int,
+              Lk: int, *, kv_shared: bool = False, accumulate: bool = False, scale: float = 0.125) -> torch.Tensor:
+    """q [B*Lq, >=H*64] (row-strided view ok), k/v [B*Lk or Lk, >=H*64] with equal strides; out [B*Lq, >=H*64]."""
+    assert k.stride(0) == v.stride(0)
+    check(lib().geo4d_attention(_vp(q), C.c_int64(q.stride(0)), _vp(k), _vp(v), C.c_int64(k.stride(0)), _vp(out),
+                                C.c_int64(out.stride(0)), B, H, Lq, Lk, 1 if kv_shared else 0,
+                                1 if accumulate else 0, C.c_float(scale), _s()), "geo4d_attention")
+    return out
+
+
+def temporal_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, B: int, T: int,
+                       HW: int, heads: int, scale: float = 0.125) -> torch.Tensor:
+    assert q.stride(0) == k.stride(0) == v.stride(0)
+    check(lib().geo4d_temporal_attention(_vp(q), _vp(k), _vp(v), C.c_int64(q.stride(0)), _vp(out),
+                                         C.c_int64(out.stride(0)), B, T, HW, heads, C.c_float(scale), _s()),
+          "geo4d_temporal_attention")
+    return out
+
+
+def bcthw_to_rows(src0: torch.Tensor, src1: Optional[torch.Tensor], Cpad: int,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    B, C0, T, H, W = src0.shape
+    C1 = 0 if src1 is None else src1.shape[1]
+    assert src0.is_contiguous() and src0.dtype == torch.float32
+    if src1 is not None:
+        assert src1.is_contiguous() and src1.dtype == torch.float32
+    if out is None:
+        out = torch.empty((B * T * H * W, Cpad), device=src0.device, dtype=torch.bfloat16)
+    check(lib().geo4d_bcthw_to_rows(_vp(src0), C0, _vp(src1), C1, B, T, H, W, _vp(out), Cpad, _s()),
+          "geo4d_bcthw_to_rows")
+    return out
+
+
+def rows_to_bcthw(rows: torch.Tensor, Cc: int, B: int, T: int, H: int, W: int,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    assert rows.dtype == torch.float32
+    if out is None:
+        out = torch.empty((B, Cc, T, H, W), device=rows.device, dtype=torch.float32)
+    check(lib().geo4d_rows_to_bcthw(_vp(rows), C.c_int64(rows.stride(0)), Cc, B, T, H, W, _vp(out), _s()),
+          "geo4d_rows_to_bcthw")
+    return out
+
+
+def concat_rows(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    rows = a.shape[0]
+    if out is None:
+        out = torch.empty((rows, a.shape[1] + b.shape[1]), device=a.device, dtype=torch.bfloat16)
+    check(lib().geo4d_concat_rows(_vp(a), C.c_int64(a.stride(0)), a.shape[1], _vp(b), C.c_int64(b.stride(0)),
+                                  b.shape[1], _vp(out), C.c_int64(rows), _s()), "geo4d_concat_rows")
+    return out
+
+
+def upsample2x(x: torch.Tensor, N: int, H: int, W: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    Cc = x.shape[1]
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty((N * 4 * H * W, Cc), device=x.device, dtype=torch.bfloat16)
+    check(lib().geo4d_upsample_nearest2x(_vp(x), _vp(out), N, H, W, Cc, _s()), "geo4d_upsample_nearest2x")
+    return out
+
+
+def im2col_s2(x: torch.Tensor, N: int, H: int, W: int, pad_before: int, Ho: int, Wo: int,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    Cc = x.shape[1]
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty((N * Ho * Wo, 9 * Cc), device=x.device, dtype=torch.bfloat16)
+    check(lib().geo4d_im2col_3x3_s2(_vp(x), _vp(out), N, H, W, Cc, pad_before, Ho, Wo, _s()),
+          "geo4d_im2col_3x3_s2")
+    return out
+
+
+def ddim_step(x: torch.Tensor, v: torch.Tensor, coef: torch.Tensor, step_idx: Optional[torch.Tensor],
+              pred_x0: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None) -> None:
+    assert x.is_contiguous() and v.is_contiguous() and x.dtype == torch.float32 and v.dtype == torch.float32
+    check(lib().geo4d_ddim_step(_vp(x), _vp(v), _vp(pred_x0), _vp(noise), _vp(coef), _vp(step_idx),
+                                C.c_int64(x.numel()), _s()), "geo4d_ddim_step")
+
+
+def advance_counter(counter: torch.Tensor, delta: int = 1, modulo: int = 0) -> None:
+    check(lib().geo4d_advance_counter(_vp(counter), delta, modulo, _s()), "geo4d_advance_counter")
+
+
+def gather_row(table: torch.Tensor, idx: torch.Tensor, out: torch.Tensor) -> None:
+    check(lib().geo4d_gather_row(_vp(table), C.c_int64(table.stride(0)), _vp(idx), _vp(out), out.numel(), _s()),
+          "geo4d_gather_row")

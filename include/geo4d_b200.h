@@ -1,0 +1,142 @@
+/*
+ * geo4d_b200 -- C ABI of the B200-native Geo4D inference hot path.
+ *
+ * The reference (jzr99/Geo4D @ 2e57abc) is pure Python/PyTorch and has NO
+ * plugin / operator / FFI interface: its seams are Python
+ * class paths named in configs/inference_geo4d.yaml and plain method calls.
+ * Each entry point below therefore names the reference call site whose
+ * arithmetic it replaces; the host-side mirrors of those Python seams live in
+ * geo4d_b200/ (same class names, arguments and state-dict keys) and reach the
+ * kernels through this library only.
+ *
+ * Conventions (all entry points):
+ *   - pointers are DEVICE pointers owned by the caller (the PyTorch caching
+ *     allocator on the Python side); the library never allocates or frees device
+ *     memory and never synchronises;
+ *   - work is enqueued on the caller-supplied stream (CUDA-graph capturable);
+ *   - return value 0 on success, negative g4 error code otherwise, with a
+ *     human readable message available from geo4d_last_error() (thread-local);
+ *   - activations are bf16 "frames-major channels-last": row (n, y, x) of a
+ *     feature map [N, H, W, C] is at ((n*H + y)*W + x) * ld + c;
+ *   - fp32 is used for statistics, accumulators, latents and all geometry.
+ */
+#ifndef GEO4D_B200_H_
+#define GEO4D_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* g4_stream_t; /* cudaStream_t */
+
+#define GEO4D_ABI_VERSION 1
+
+int geo4d_abi_version(void);
+const char* geo4d_last_error(void);
+/* 1 if the current device is compute capability 10.x (tcgen05/TMEM present). */
+int geo4d_device_supported(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tap-GEMM on tcgen05 tensor cores (TMA -> shared memory -> tcgen05.mma -> TMEM -> epilogue).
+ *
+ *   out[(n,y,x), j] = epilogue( sum_{tap} sum_{c<K} A[n, y+dy[tap], x+dx[tap], c] * B[tap, j, c] )
+ *
+ * with zero padding outside [0,W)x[0,H).  One kernel covers every dense contraction of the path:
+ *   - nn.Linear / 1x1 conv (to_q/to_k/to_v/to_out, proj_in/out, GEGLU, FF; attention.py:54-59,262-290,
+ *     415-442; ae_modules.py nin_shortcut/AttnBlock q,k,v,proj_out):              num_taps = 1
+ *   - 3x3 Conv2d, padding 1 (ResBlock in/out layers openaimodel3d.py:151-180, Upsample conv :98-106,
+ *     VAE ResnetBlock/conv_in/conv_out ae_modules.py:189-248,604-659):             num_taps = 9
+ *   - Conv3d (3,1,1), padding (1,0,0) (TemporalConvBlock openaimodel3d.py:255-279): num_taps = 3
+ *     (view the tensor as W = h*w pixels, H = frames, N = batch)
+ *   - batched matmul (VAE AttnBlock q k^T / p v, ae_modules.py:63-73):             b_batched = 1
+ * K (= C) must be a multiple of 64 (pad the channel dim with zeros otherwise).
+ * ---------------------------------------------------------------------------------------------- */
+enum { G4_ACT_NONE = 0, G4_ACT_SILU = 1, G4_ACT_GEGLU = 2 };
+
+typedef struct {
+  /* A operand, bf16 */
+  const void* a;
+  int K;                     /* channels (multiple of 64)                         */
+  int W, H, N;               /* logical extents                                    */
+  int64_t a_stride_w, a_stride_h, a_stride_n; /* in elements                       */
+  int box_w, box_h, box_n;   /* M tile = box_w*box_h*box_n rows, <= 128            */
+  int num_taps;              /* 1..9                                               */
+  int tap_dx[9], tap_dy[9];
+  /* B operand, bf16 [num_taps][n_out][K] (K contiguous); if b_batched, [N][n_out][K]
+   * and the matrix used is selected by the row tile's n index (box_n must be 1). */
+  const void* b;
+  int n_out;
+  int b_batched;
+  /* output: bf16 (or fp32 if out_fp32) at out + row*ldc + col, row = (n*H + y)*W + x.
+   * For G4_ACT_GEGLU the stored width is n_out/2 (B rows interleaved in blocks of 32:
+   * 32 value rows followed by their 32 gate rows). */
+  void* out;
+  int64_t ldc;
+  int out_fp32;
+  float alpha;               /* accumulator scale applied first                    */
+  const float* bias;         /* [n_out] fp32 or NULL                               */
+  const float* row_bias;     /* fp32 [*, row_bias_ld]: added as row_bias[(row / rows_per_bias)][col] */
+  int64_t row_bias_ld;
+  int rows_per_bias;
+  int act;
+  const void* residual;      /* bf16, same row indexing with ldr, added last; may alias out */
+  int64_t ldr;
+} g4_gemm_desc;
+
+int geo4d_tap_gemm(const g4_gemm_desc* d, g4_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused softmax attention, head dim 64, non-causal, tcgen05 (S = QK^T and O = PV on tensor cores,
+ * scores stay in TMEM/registers).  Replaces xformers.ops.memory_efficient_attention as called from
+ * CrossAttention.efficient_forward (attention.py:146-209; einsum fallback :101-125).
+ *   q   : bf16 [B*Lq rows, ldq]   head h at columns [h*64, h*64+64)
+ *   k,v : bf16 [B*Lk rows, ldkv]  (kv_shared: [Lk rows], same keys for every batch entry)
+ *   out : bf16 [B*Lq rows, ldo];  accumulate != 0 adds to the existing contents (second
+ *         cross-attention branch, attention.py:203-207).
+ * ---------------------------------------------------------------------------------------------- */
+int geo4d_attention(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* out,
+                    int64_t ldo, int B, int H, int Lq, int Lk, int kv_shared, int accumulate, float scale,
+                    g4_stream_t stream);
+
+/* Temporal self-attention over <=16 frame tokens per (pixel, head) (CrossAttention.forward
+ * attention.py:81-144 as used by TemporalTransformer :365-412).  Row of (b, t, p) = (b*T + t)*HW + p. */
+int geo4d_temporal_attention(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo,
+                             int B, int T, int HW, int heads, float scale, g4_stream_t stream);
+
+/* GroupNorm(32) [+SiLU] over `rows_per_stat` consecutive rows per statistic (basics.py:76-87,
+ * openaimodel3d.py:151-155,175-180,256-266; attention.py:265,331; ae_modules.py:14-15). */
+size_t geo4d_groupnorm_workspace_bytes(int num_stats);
+int geo4d_groupnorm_silu(const void* x, int64_t ldx, void* y, int64_t ldy, int num_stats, int rows_per_stat,
+                         int C, const float* gamma, const float* beta, float eps, int apply_silu,
+                         void* workspace, size_t workspace_bytes, g4_stream_t stream);
+/* nn.LayerNorm over C per row (attention.py:229-231). */
+int geo4d_layernorm(const void* x, int64_t ldx, void* y, int64_t ldy, int M, int C, const float* gamma,
+                    const float* beta, float eps, g4_stream_t stream);
+
+/* Layout / data movement (einops rearranges + torch.cat of openaimodel3d.py:588,627,633; ddpm3d.py:2541;
+ * F.interpolate nearest x2 :98-106; stride-2 convs :66-77 and ae_modules.py:100-109 via im2col). */
+int geo4d_bcthw_to_rows(const float* src0, int C0, const float* src1, int C1, int B, int T, int H, int W,
+                        void* out_bf16, int Cpad, g4_stream_t stream);
+int geo4d_rows_to_bcthw(const float* rows, int64_t ld, int C, int B, int T, int H, int W, float* out,
+                        g4_stream_t stream);
+int geo4d_concat_rows(const void* a, int64_t lda, int Ca, const void* b, int64_t ldb, int Cb, void* out,
+                      int64_t rows, g4_stream_t stream);
+int geo4d_upsample_nearest2x(const void* in, void* out, int N, int H, int W, int C, g4_stream_t stream);
+int geo4d_im2col_3x3_s2(const void* in, void* out, int N, int H, int W, int C, int pad_before, int Ho, int Wo,
+                        g4_stream_t stream);
+
+/* DDIM update for the v-parameterisation (DDIMSampler.p_sample_ddim ddim.py:231-277;
+ * predict_start/eps_from_z_and_v ddpm3d.py:278-290).  coef[step] = {sqrt(abar_t), sqrt(1-abar_t),
+ * scale_prev/scale_t, sqrt(a_prev), sqrt(1-a_prev-sigma^2), sigma}; step = *step_idx (device). */
+int geo4d_ddim_step(float* x, const float* v, float* pred_x0, const float* noise, const float* coef,
+                    const int* step_idx, int64_t n, g4_stream_t stream);
+int geo4d_advance_counter(int* counter, int delta, int modulo, g4_stream_t stream);
+int geo4d_gather_row(const float* table, int64_t ld, const int* idx, float* out, int n, g4_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEO4D_B200_H_ */
