@@ -22,7 +22,7 @@ namespace g4 {
 struct AttnArgs {
   int B, H, Lq, Lk;
   int n_qtiles, n_kvtiles;
-  int kv_shared;
+  int kv_batch_div;  // K/V batch index = b / kv_batch_div (text keys shared by the frames of a clip)
   int accumulate;
   float scale_log2;  // scale * log2(e)
   void* out;
@@ -58,7 +58,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int bh = blockIdx.x / args.n_qtiles;
   const int h = bh % args.H;
   const int b = bh / args.H;
-  const int bkv = args.kv_shared ? 0 : b;
+  const int bkv = b / args.kv_batch_div;
   const int nkv = args.n_kvtiles;
 
   if (threadIdx.x == 0) {
@@ -271,11 +271,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 using namespace g4;
 
 extern "C" int geo4d_attention(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* out,
-                               int64_t ldo, int B, int H, int Lq, int Lk, int kv_shared, int accumulate, float scale,
+                               int64_t ldo, int B, int H, int Lq, int Lk, int kv_batch_div, int accumulate, float scale,
                                g4_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!q || !k || !v || !out) { set_last_error("attention: null pointer"); return G4_ERR_BAD_ARG; }
-  if (B < 1 || H < 1 || Lq < 1 || Lk < 1) { set_last_error("attention: bad sizes B=%d H=%d Lq=%d Lk=%d", B, H, Lq, Lk); return G4_ERR_BAD_ARG; }
+  if (B < 1 || H < 1 || Lq < 1 || Lk < 1 || kv_batch_div < 1) { set_last_error("attention: bad sizes B=%d H=%d Lq=%d Lk=%d", B, H, Lq, Lk); return G4_ERR_BAD_ARG; }
   if (ldq % 8 || ldkv % 8 || ldo % 8 || ((uintptr_t)q & 15) || ((uintptr_t)k & 15) || ((uintptr_t)v & 15) ||
       ((uintptr_t)out & 15)) {
     set_last_error("attention: pointers must be 16-byte aligned and leading dims multiples of 8"); return G4_ERR_BAD_ARG;
@@ -289,7 +289,7 @@ extern "C" int geo4d_attention(const void* q, int64_t ldq, const void* k, const 
     if (rc) return rc;
   }
   {
-    uint64_t dims[4] = {64, (uint64_t)H, (uint64_t)Lk, (uint64_t)(kv_shared ? 1 : B)};
+    uint64_t dims[4] = {64, (uint64_t)H, (uint64_t)Lk, (uint64_t)((B + kv_batch_div - 1) / kv_batch_div)};
     uint64_t str[3] = {128, (uint64_t)ldkv * 2, (uint64_t)ldkv * 2 * (uint64_t)Lk};
     uint32_t box[4] = {64, 1, 128, 1};
     int rc = make_tmap_bf16(&tmK, k, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -301,7 +301,7 @@ extern "C" int geo4d_attention(const void* q, int64_t ldq, const void* k, const 
   a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk;
   a.n_qtiles = (Lq + 127) / 128;
   a.n_kvtiles = (Lk + 127) / 128;
-  a.kv_shared = kv_shared; a.accumulate = accumulate;
+  a.kv_batch_div = kv_batch_div; a.accumulate = accumulate;
   a.scale_log2 = scale * 1.4426950408889634f;
   a.out = out; a.ldo = ldo;
   static bool attr_set = false;

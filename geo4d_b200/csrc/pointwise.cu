@@ -137,6 +137,59 @@ __global__ void gather_row_kernel(const float* __restrict__ table, long long ld,
     out[j] = table[(long long)s * ld + j];
 }
 
+
+// ---------------------------------------------------------------------------------------------- VAE AttnBlock helpers
+// row softmax: fp32 scores -> bf16 probabilities (ae_modules.py:66-67); one warp per row.
+__global__ void softmax_rows_kernel(const float* __restrict__ s, long long lds, __nv_bfloat16* __restrict__ p,
+                                    long long ldp, long long rows, int cols) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* sr = s + row * lds;
+  float mx = -INFINITY;
+  for (int c = lane * 4; c < cols; c += 128) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(sr + c));
+    mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int c = lane * 4; c < cols; c += 128) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(sr + c));
+    sum += __expf(v.x - mx) + __expf(v.y - mx) + __expf(v.z - mx) + __expf(v.w - mx);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.0f / sum;
+  __nv_bfloat16* pr = p + row * ldp;
+  for (int c = lane * 4; c < cols; c += 128) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(sr + c));
+    uint2 w;
+    w.x = pack_bf16x2(__expf(v.x - mx) * inv, __expf(v.y - mx) * inv);
+    w.y = pack_bf16x2(__expf(v.z - mx) * inv, __expf(v.w - mx) * inv);
+    *reinterpret_cast<uint2*>(pr + c) = w;
+  }
+}
+
+// out[b, c, r] = in[b, r, c] (bf16), 32x32 tiles through shared memory
+__global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, long long ldin,
+                                      __nv_bfloat16* __restrict__ out, int R, int Cc) {
+  __shared__ __nv_bfloat16 tile[32][34];
+  const int b = blockIdx.z;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const __nv_bfloat16* ib = in + (long long)b * R * ldin;
+  __nv_bfloat16* ob = out + (long long)b * Cc * R;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < R && c < Cc) tile[i][threadIdx.x] = ib[(long long)r * ldin + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < Cc) ob[(long long)c * R + r] = tile[threadIdx.x][i];
+  }
+}
+
 static inline int grid_for(long long total, int block, int cap) {
   long long g = (total + block - 1) / block;
   if (g > cap) g = cap;
@@ -229,4 +282,25 @@ extern "C" int geo4d_gather_row(const float* table, int64_t ld, const int* idx, 
   if (!table || !idx || !out) { set_last_error("gather_row: null"); return G4_ERR_BAD_ARG; }
   gather_row_kernel<<<grid_for(n, 256, 64), 256, 0, stream>>>(table, ld, idx, out, n);
   return check_launch("gather_row");
+}
+
+extern "C" int geo4d_softmax_rows(const float* s, int64_t lds, void* p, int64_t ldp, int64_t rows, int cols,
+                                  g4_stream_t stream_) {
+  G4_STREAM;
+  if (!s || !p || cols % 4 || lds % 4 || ldp % 4 || ((uintptr_t)s & 15) || ((uintptr_t)p & 7)) {
+    set_last_error("softmax_rows: cols/ld must be multiples of 4 and pointers aligned"); return G4_ERR_BAD_ARG;
+  }
+  const long long blocks = (rows + 7) / 8;
+  softmax_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(s, lds, reinterpret_cast<__nv_bfloat16*>(p), ldp, rows, cols);
+  return check_launch("softmax_rows");
+}
+
+extern "C" int geo4d_transpose_bf16(const void* in, int64_t ldin, void* out, int batch, int R, int Cc,
+                                    g4_stream_t stream_) {
+  G4_STREAM;
+  if (!in || !out || batch < 1 || batch > 65535) { set_last_error("transpose: bad args"); return G4_ERR_BAD_ARG; }
+  dim3 grid((Cc + 31) / 32, (R + 31) / 32, batch), block(32, 8);
+  transpose_bf16_kernel<<<grid, block, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), ldin,
+                                                    reinterpret_cast<__nv_bfloat16*>(out), R, Cc);
+  return check_launch("transpose_bf16");
 }

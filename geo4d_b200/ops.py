@@ -184,11 +184,11 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, B: int, H: int, Lq: int,
-              Lk: int, *, kv_shared: bool = False, accumulate: bool = False, scale: float = 0.125) -> torch.Tensor:
-    """q [B*Lq, >=H*64] (row-strided view ok), k/v [B*Lk or Lk, >=H*64] with equal strides; out [B*Lq, >=H*64]."""
+              Lk: int, *, kv_batch_div: int = 1, accumulate: bool = False, scale: float = 0.125) -> torch.Tensor:
+    """q [B*Lq, >=H*64] (row-strided view ok), k/v [ceil(B/kv_batch_div)*Lk, >=H*64] with equal strides; out [B*Lq, >=H*64]."""
     assert k.stride(0) == v.stride(0)
     check(lib().geo4d_attention(_vp(q), C.c_int64(q.stride(0)), _vp(k), _vp(v), C.c_int64(k.stride(0)), _vp(out),
-                                C.c_int64(out.stride(0)), B, H, Lq, Lk, 1 if kv_shared else 0,
+                                C.c_int64(out.stride(0)), B, H, Lq, Lk, kv_batch_div,
                                 1 if accumulate else 0, C.c_float(scale), _s()), "geo4d_attention")
     return out
 
@@ -269,3 +269,22 @@ def advance_counter(counter: torch.Tensor, delta: int = 1, modulo: int = 0) -> N
 def gather_row(table: torch.Tensor, idx: torch.Tensor, out: torch.Tensor) -> None:
     check(lib().geo4d_gather_row(_vp(table), C.c_int64(table.stride(0)), _vp(idx), _vp(out), out.numel(), _s()),
           "geo4d_gather_row")
+
+
+def softmax_rows(scores: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Row softmax of fp32 [rows, cols] -> bf16 probabilities."""
+    rows, cols = scores.shape
+    if out is None:
+        out = torch.empty((rows, cols), device=scores.device, dtype=torch.bfloat16)
+    check(lib().geo4d_softmax_rows(_vp(scores), C.c_int64(scores.stride(0)), _vp(out), C.c_int64(out.stride(0)),
+                                   C.c_int64(rows), cols, _s()), "geo4d_softmax_rows")
+    return out
+
+
+def transpose_bf16(x: torch.Tensor, batch: int, R: int, Cc: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x rows [batch*R, >=Cc] (row stride ld) -> out [batch, Cc, R] contiguous."""
+    if out is None:
+        out = torch.empty((batch, Cc, R), device=x.device, dtype=torch.bfloat16)
+    check(lib().geo4d_transpose_bf16(_vp(x), C.c_int64(x.stride(0)), _vp(out), batch, R, Cc, _s()),
+          "geo4d_transpose_bf16")
+    return out

@@ -1,0 +1,602 @@
+"""B200-native spatio-temporal U-Net behind the reference's `UNetModel` seam.
+
+Drop-in for lvdm/modules/networks/openaimodel3d.py:UNetModel (constructor
+arguments = `unet_config.params` of configs/inference_geo4d.yaml:62-89,
+`forward(x, timesteps, context=None, fs=None)` as at :558-633, identical
+`state_dict()` keys so the reference checkpoint loads with strict=True).
+
+The module keeps the reference parameter tree only as a container for the
+checkpoint tensors; `prepare()` repacks them once into the kernel layouts
+(bf16, [taps, Cout, Cin] conv weights, fused qkv, block-interleaved GEGLU ...)
+and the forward pass is a flat sequence of C-ABI kernel launches on bf16
+"rows" tensors ([frames*h*w, C], channels-last) -- no einops rearranges, no
+head-split copies, cross-attention K/V cached per context.  There is no
+PyTorch fallback: without libgeo4d_b200.so / a B200 this module raises.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._cabi import require_device
+
+
+# --------------------------------------------------------------------------- architecture plan
+def _build_plan(in_channels, model_channels, channel_mult, num_res_blocks, attention_resolutions,
+                num_head_channels, temporal_conv, temporal_attention, use_linear):
+    """Block list equivalent to UNetModel.__init__ (openaimodel3d.py:385-556)."""
+    mc = model_channels
+    inp = [[("conv", "input_blocks.0.0", in_channels, mc)]]
+    chans, ch, ds, idx = [mc], mc, 1, 1
+    for level, mult in enumerate(channel_mult):
+        for _ in range(num_res_blocks):
+            layers = [("res", f"input_blocks.{idx}.0", ch, mult * mc, temporal_conv)]
+            ch = mult * mc
+            if ds in attention_resolutions:
+                heads = ch // num_head_channels
+                layers.append(("st", f"input_blocks.{idx}.1", ch, heads))
+                if temporal_attention:
+                    layers.append(("tt", f"input_blocks.{idx}.2", ch, heads, use_linear))
+            inp.append(layers)
+            chans.append(ch)
+            idx += 1
+        if level != len(channel_mult) - 1:
+            inp.append([("down", f"input_blocks.{idx}.0", ch, ch)])
+            chans.append(ch)
+            ds *= 2
+            idx += 1
+    heads = ch // num_head_channels
+    mid = [("res", "middle_block.0", ch, ch, temporal_conv), ("st", "middle_block.1", ch, heads)]
+    if temporal_attention:
+        mid.append(("tt", "middle_block.2", ch, heads, use_linear))
+    mid.append(("res", f"middle_block.{len(mid)}", ch, ch, temporal_conv))
+    out, idx = [], 0
+    for level, mult in list(enumerate(channel_mult))[::-1]:
+        for i in range(num_res_blocks + 1):
+            ich = chans.pop()
+            layers = [("res", f"output_blocks.{idx}.0", ch + ich, mc * mult, temporal_conv)]
+            ch = mc * mult
+            if ds in attention_resolutions:
+                heads = ch // num_head_channels
+                layers.append(("st", f"output_blocks.{idx}.1", ch, heads))
+                if temporal_attention:
+                    layers.append(("tt", f"output_blocks.{idx}.2", ch, heads, use_linear))
+            if level and i == num_res_blocks:
+                layers.append(("up", f"output_blocks.{idx}.{len(layers)}", ch, ch))
+                ds //= 2
+            out.append(layers)
+            idx += 1
+    return inp, mid, out, ch
+
+
+class _Node(nn.Module):
+    """Anonymous container used to reproduce the reference's dotted parameter names."""
+
+
+def _register(root: nn.Module, name: str, tensor: torch.Tensor):
+    parts = name.split(".")
+    mod = root
+    for p in parts[:-1]:
+        if not hasattr(mod, p):
+            mod.add_module(p, _Node())
+        mod = getattr(mod, p)
+    mod.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=False))
+
+
+def _pad_k(w: torch.Tensor, k_to: int) -> torch.Tensor:
+    if w.shape[-1] == k_to:
+        return w
+    out = w.new_zeros(*w.shape[:-1], k_to)
+    out[..., : w.shape[-1]] = w
+    return out
+
+
+def _interleave32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """rows of a / b -> [a0..a31, b0..b31, a32..a63, b32..b63, ...] (GEGLU epilogue layout)."""
+    n = a.shape[0]
+    return torch.stack([a.reshape(n // 32, 32, *a.shape[1:]), b.reshape(n // 32, 32, *b.shape[1:])], 1) \
+        .reshape(2 * n, *a.shape[1:]).contiguous()
+
+
+def timestep_embedding(timesteps: torch.Tensor, dim: int, max_period: int = 10000) -> torch.Tensor:
+    """Sinusoidal embedding, cos first then sin (utils_diffusion.py:8-28)."""
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half) \
+        .to(timesteps.device)
+    args = timesteps[:, None].float() * freqs[None]
+    emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+    if dim % 2:
+        emb = torch.cat([emb, torch.zeros_like(emb[:, :1])], dim=-1)
+    return emb
+
+
+class UNetModel(nn.Module):
+    def __init__(self, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions,
+                 dropout=0.0, channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, context_dim=None,
+                 use_scale_shift_norm=False, resblock_updown=False, num_heads=-1, num_head_channels=-1,
+                 transformer_depth=1, use_linear=False, use_checkpoint=False, temporal_conv=False,
+                 tempspatial_aware=False, temporal_attention=True, use_relative_position=True,
+                 use_causal_attention=False, temporal_length=None, use_fp16=False, addition_attention=False,
+                 temporal_selfatt_only=True, image_cross_attention=False,
+                 image_cross_attention_scale_learnable=False, default_fs=4, fs_condition=False,
+                 task_condition=False):
+        super().__init__()
+        unsupported = dict(use_scale_shift_norm=use_scale_shift_norm, resblock_updown=resblock_updown,
+                           tempspatial_aware=tempspatial_aware, use_relative_position=use_relative_position,
+                           use_causal_attention=use_causal_attention, task_condition=task_condition,
+                           image_cross_attention_scale_learnable=image_cross_attention_scale_learnable)
+        bad = [k for k, v in unsupported.items() if v]
+        if bad or dims != 2 or not conv_resample or num_head_channels != 64 or transformer_depth != 1 \
+                or not use_linear or not temporal_selfatt_only:
+            raise NotImplementedError(
+                "geo4d_b200.UNetModel implements the Geo4D inference configuration "
+                f"(configs/inference_geo4d.yaml); unsupported options: {bad or 'see source'}")
+        self.in_channels = in_channels
+        self.model_channels = model_channels
+        self.out_channels = out_channels
+        self.num_res_blocks = num_res_blocks
+        self.attention_resolutions = tuple(attention_resolutions)
+        self.channel_mult = tuple(channel_mult)
+        self.context_dim = context_dim
+        self.temporal_length = temporal_length
+        self.addition_attention = addition_attention
+        self.image_cross_attention = image_cross_attention
+        self.default_fs = default_fs
+        self.fs_condition = fs_condition
+        self.temporal_conv = temporal_conv
+        self.temporal_attention = temporal_attention
+        self.use_checkpoint = use_checkpoint  # accepted for config parity; inference only
+        self.dtype = torch.float32
+        self.text_context_len = 77
+        self.init_attn_heads = 8  # openaimodel3d.py:403
+        self.plan = _build_plan(in_channels, model_channels, self.channel_mult, num_res_blocks,
+                                self.attention_resolutions, num_head_channels, temporal_conv,
+                                temporal_attention, use_linear)
+        for k, shp in self._param_shapes().items():
+            _register(self, k, torch.empty(shp))
+        self._packed = None
+        self._ctx_cache = None
+
+    # ------------------------------------------------------------------ parameter inventory
+    def _param_shapes(self) -> "OrderedDict[str, tuple]":
+        mc, emb, dh = self.model_channels, self.model_channels * 4, 64
+        cd = self.context_dim
+        s = OrderedDict()
+
+        def lin(p, n, k, bias=True):
+            s[f"{p}.weight"] = (n, k)
+            if bias:
+                s[f"{p}.bias"] = (n,)
+
+        def attn(p, dim, heads, ctx, ip):
+            inner = heads * dh
+            lin(f"{p}.to_q", inner, dim, False)
+            lin(f"{p}.to_k", inner, ctx, False)
+            lin(f"{p}.to_v", inner, ctx, False)
+            lin(f"{p}.to_out.0", dim, inner)
+            if ip:
+                lin(f"{p}.to_k_ip", inner, ctx, False)
+                lin(f"{p}.to_v_ip", inner, ctx, False)
+
+        def btb(p, dim, heads, ctx, ip):
+            attn(f"{p}.attn1", dim, heads, dim, False)
+            lin(f"{p}.ff.net.0.proj", dim * 8, dim)
+            lin(f"{p}.ff.net.2", dim, dim * 4)
+            attn(f"{p}.attn2", dim, heads, ctx if ctx else dim, ip)
+            for n in ("norm1", "norm2", "norm3"):
+                s[f"{p}.{n}.weight"] = (dim,)
+                s[f"{p}.{n}.bias"] = (dim,)
+
+        def tt(p, ch, heads, use_linear):
+            inner = heads * dh
+            s[f"{p}.norm.weight"] = (ch,)
+            s[f"{p}.norm.bias"] = (ch,)
+            s[f"{p}.proj_in.weight"] = (inner, ch) if use_linear else (inner, ch, 1)
+            s[f"{p}.proj_in.bias"] = (inner,)
+            btb(f"{p}.transformer_blocks.0", inner, heads, None, False)
+            s[f"{p}.proj_out.weight"] = (ch, inner) if use_linear else (ch, inner, 1)
+            s[f"{p}.proj_out.bias"] = (ch,)
+
+        def add(layers):
+            for L in layers:
+                kind, p = L[0], L[1]
+                if kind == "conv":
+                    s[f"{p}.weight"] = (L[3], L[2], 3, 3)
+                    s[f"{p}.bias"] = (L[3],)
+                elif kind == "res":
+                    cin, cout = L[2], L[3]
+                    s[f"{p}.in_layers.0.weight"] = (cin,)
+                    s[f"{p}.in_layers.0.bias"] = (cin,)
+                    s[f"{p}.in_layers.2.weight"] = (cout, cin, 3, 3)
+                    s[f"{p}.in_layers.2.bias"] = (cout,)
+                    lin(f"{p}.emb_layers.1", cout, emb)
+                    s[f"{p}.out_layers.0.weight"] = (cout,)
+                    s[f"{p}.out_layers.0.bias"] = (cout,)
+                    s[f"{p}.out_layers.3.weight"] = (cout, cout, 3, 3)
+                    s[f"{p}.out_layers.3.bias"] = (cout,)
+                    if cin != cout:
+                        s[f"{p}.skip_connection.weight"] = (cout, cin, 1, 1)
+                        s[f"{p}.skip_connection.bias"] = (cout,)
+                    if L[4]:
+                        for k, ci in (("conv1", 2), ("conv2", 3), ("conv3", 3), ("conv4", 3)):
+                            s[f"{p}.temopral_conv.{k}.0.weight"] = (cout,)
+                            s[f"{p}.temopral_conv.{k}.0.bias"] = (cout,)
+                            s[f"{p}.temopral_conv.{k}.{ci}.weight"] = (cout, cout, 3, 1, 1)
+                            s[f"{p}.temopral_conv.{k}.{ci}.bias"] = (cout,)
+                elif kind == "st":
+                    ch, heads = L[2], L[3]
+                    inner = heads * dh
+                    s[f"{p}.norm.weight"] = (ch,)
+                    s[f"{p}.norm.bias"] = (ch,)
+                    lin(f"{p}.proj_in", inner, ch)
+                    btb(f"{p}.transformer_blocks.0", inner, heads, cd, self.image_cross_attention)
+                    lin(f"{p}.proj_out", ch, inner)
+                elif kind == "tt":
+                    tt(p, L[2], L[3], L[4])
+                elif kind == "down":
+                    s[f"{p}.op.weight"] = (L[3], L[2], 3, 3)
+                    s[f"{p}.op.bias"] = (L[3],)
+                elif kind == "up":
+                    s[f"{p}.conv.weight"] = (L[3], L[2], 3, 3)
+                    s[f"{p}.conv.bias"] = (L[3],)
+
+        for name in ("time_embed",) + (("fps_embedding",) if self.fs_condition else ()):
+            lin(f"{name}.0", emb, mc)
+            lin(f"{name}.2", emb, emb)
+        inp, mid, out, final_ch = self.plan
+        for layers in inp:
+            add(layers)
+        if self.addition_attention:
+            tt("init_attn.0", mc, self.init_attn_heads, False)
+        add(mid)
+        for layers in out:
+            add(layers)
+        s["out.0.weight"] = (final_ch,)
+        s["out.0.bias"] = (final_ch,)
+        s["out.2.weight"] = (self.out_channels, mc, 3, 3)
+        s["out.2.bias"] = (self.out_channels,)
+        return s
+
+    # ------------------------------------------------------------------ weight packing
+    def _load_from_state_dict(self, *a, **k):
+        self._packed = None
+        self._ctx_cache = None
+        return super()._load_from_state_dict(*a, **k)
+
+    @torch.no_grad()
+    def prepare(self, free_fp32: bool = False):
+        """Repack the checkpoint tensors into kernel layouts on the current CUDA device."""
+        require_device()
+        sd = {k: v.detach() for k, v in self.state_dict().items()}
+        dev = next(iter(sd.values())).device
+        if dev.type != "cuda":
+            raise RuntimeError("UNetModel.prepare(): move the model to a CUDA device first (.cuda())")
+        P: Dict[str, torch.Tensor] = {}
+        bf = lambda t: t.to(torch.bfloat16).contiguous()
+        f32 = lambda t: t.float().contiguous()
+
+        def conv9(p, cin_pad=None):
+            w = sd[f"{p}.weight"]
+            co, ci = w.shape[0], w.shape[1]
+            w9 = w.permute(2, 3, 0, 1).reshape(9, co, ci)
+            if cin_pad:
+                w9 = _pad_k(w9, cin_pad)
+            P[f"{p}.w"] = bf(w9)
+            P[f"{p}.b"] = f32(sd[f"{p}.bias"])
+
+        def lin(p, bias=True):
+            P[f"{p}.w"] = bf(sd[f"{p}.weight"].reshape(sd[f"{p}.weight"].shape[0], -1))
+            if bias:
+                P[f"{p}.b"] = f32(sd[f"{p}.bias"])
+
+        def norm(p):
+            P[f"{p}.g"] = f32(sd[f"{p}.weight"])
+            P[f"{p}.be"] = f32(sd[f"{p}.bias"])
+
+        def btb(p, cross):
+            a1 = f"{p}.attn1"
+            P[f"{a1}.qkv"] = bf(torch.cat([sd[f"{a1}.to_q.weight"], sd[f"{a1}.to_k.weight"],
+                                            sd[f"{a1}.to_v.weight"]], 0))
+            lin(f"{a1}.to_out.0")
+            a2 = f"{p}.attn2"
+            if cross:
+                P[f"{a2}.q"] = bf(sd[f"{a2}.to_q.weight"])
+                P[f"{a2}.kv"] = bf(torch.cat([sd[f"{a2}.to_k.weight"], sd[f"{a2}.to_v.weight"]], 0))
+                if self.image_cross_attention:
+                    P[f"{a2}.kv_ip"] = bf(torch.cat([sd[f"{a2}.to_k_ip.weight"], sd[f"{a2}.to_v_ip.weight"]], 0))
+            else:
+                P[f"{a2}.qkv"] = bf(torch.cat([sd[f"{a2}.to_q.weight"], sd[f"{a2}.to_k.weight"],
+                                                sd[f"{a2}.to_v.weight"]], 0))
+            lin(f"{a2}.to_out.0")
+            w = sd[f"{p}.ff.net.0.proj.weight"]
+            b = sd[f"{p}.ff.net.0.proj.bias"]
+            h = w.shape[0] // 2
+            P[f"{p}.ff.w1"] = bf(_interleave32(w[:h], w[h:]))
+            P[f"{p}.ff.b1"] = f32(_interleave32(b[:h], b[h:]))
+            lin(f"{p}.ff.net.2")
+            for n in ("norm1", "norm2", "norm3"):
+                norm(f"{p}.{n}")
+
+        emb_w, emb_b, self._emb_slices, off = [], [], {}, 0
+
+        def res(L):
+            nonlocal off
+            p, cin, cout, tconv = L[1], L[2], L[3], L[4]
+            norm(f"{p}.in_layers.0")
+            conv9(f"{p}.in_layers.2")
+            norm(f"{p}.out_layers.0")
+            conv9(f"{p}.out_layers.3")
+            emb_w.append(sd[f"{p}.emb_layers.1.weight"])
+            emb_b.append(sd[f"{p}.emb_layers.1.bias"])
+            self._emb_slices[p] = (off, cout)
+            off += cout
+            if cin != cout:
+                lin(f"{p}.skip_connection")
+            if tconv:
+                for k, ci in (("conv1", 2), ("conv2", 3), ("conv3", 3), ("conv4", 3)):
+                    q = f"{p}.temopral_conv.{k}"
+                    norm(f"{q}.0")
+                    w = sd[f"{q}.{ci}.weight"]
+                    P[f"{q}.w"] = bf(w[:, :, :, 0, 0].permute(2, 0, 1))
+                    P[f"{q}.b"] = f32(sd[f"{q}.{ci}.bias"])
+
+        def pack(layers):
+            for L in layers:
+                kind, p = L[0], L[1]
+                if kind == "conv":
+                    conv9(p, cin_pad=-(-L[2] // 64) * 64)
+                elif kind == "res":
+                    res(L)
+                elif kind == "st":
+                    norm(f"{p}.norm")
+                    lin(f"{p}.proj_in")
+                    btb(f"{p}.transformer_blocks.0", True)
+                    lin(f"{p}.proj_out")
+                elif kind == "tt":
+                    norm(f"{p}.norm")
+                    lin(f"{p}.proj_in")
+                    btb(f"{p}.transformer_blocks.0", False)
+                    lin(f"{p}.proj_out")
+                elif kind == "down":
+                    w = sd[f"{p}.op.weight"]  # [co, ci, 3, 3] -> [co, (ky kx ci)]
+                    P[f"{p}.w"] = bf(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1))
+                    P[f"{p}.b"] = f32(sd[f"{p}.op.bias"])
+                elif kind == "up":
+                    w = sd[f"{p}.conv.weight"]
+                    P[f"{p}.w"] = bf(w.permute(2, 3, 0, 1).reshape(9, w.shape[0], w.shape[1]))
+                    P[f"{p}.b"] = f32(sd[f"{p}.conv.bias"])
+
+        for name in ("time_embed",) + (("fps_embedding",) if self.fs_condition else ()):
+            lin(f"{name}.0")
+            lin(f"{name}.2")
+        inp, mid, out, _ = self.plan
+        for layers in inp:
+            pack(layers)
+        if self.addition_attention:
+            p = "init_attn.0"
+            norm(f"{p}.norm")
+            lin(f"{p}.proj_in")
+            btb(f"{p}.transformer_blocks.0", False)
+            lin(f"{p}.proj_out")
+        pack(mid)
+        for layers in out:
+            pack(layers)
+        norm("out.0")
+        conv9("out.2")
+        P["emb_all.w"] = bf(torch.cat(emb_w, 0))
+        P["emb_all.b"] = f32(torch.cat(emb_b, 0))
+        self._emb_total = off
+        self._packed = P
+        self._ctx_cache = None
+        if free_fp32:
+            for prm in self.parameters():
+                prm.data = torch.empty(0, device=dev)
+        return self
+
+    # ------------------------------------------------------------------ conditioning
+    @torch.no_grad()
+    def embed(self, timesteps: torch.Tensor, fs: Optional[torch.Tensor], b: int) -> torch.Tensor:
+        """emb -> per-ResBlock `emb_layers` outputs, fp32 [b, sum(Cout)] (openaimodel3d.py:569-599,
+        ResBlock emb_layers :167-173).  All 22 Linear(1280->Cout) run as one GEMM."""
+        P = self._packed
+        mc = self.model_channels
+        dev = P["emb_all.w"].device
+        t_emb = timestep_embedding(timesteps.to(dev), mc).to(torch.bfloat16)
+        h = ops.linear(t_emb, P["time_embed.0.w"], P["time_embed.0.b"], act=ops.ACT_SILU)
+        emb = ops.linear(h, P["time_embed.2.w"], P["time_embed.2.b"], out_dtype=torch.float32)
+        if self.fs_condition:
+            if fs is None:
+                fs = torch.full((b,), self.default_fs, dtype=torch.long, device=dev)
+            f_emb = timestep_embedding(fs.to(dev), mc).to(torch.bfloat16)
+            h = ops.linear(f_emb, P["fps_embedding.0.w"], P["fps_embedding.0.b"], act=ops.ACT_SILU)
+            emb = emb + ops.linear(h, P["fps_embedding.2.w"], P["fps_embedding.2.b"], out_dtype=torch.float32)
+        if emb.shape[0] != b:
+            emb = emb.expand(b, -1)
+        e = torch.nn.functional.silu(emb).to(torch.bfloat16).contiguous()
+        return ops.linear(e, P["emb_all.w"], P["emb_all.b"], out_dtype=torch.float32)
+
+    @torch.no_grad()
+    def set_context(self, context: torch.Tensor, t: int):
+        """Project the (constant) conditioning tokens once: text K/V [b*77, 2*inner] and per-frame image
+        K/V [(b t)*16, 2*inner] for every spatial transformer (attention.py:154-164)."""
+        P = self._packed
+        b, l_ctx, cd = context.shape
+        tl = self.text_context_len
+        if l_ctx == tl + t * 16:  # hard-coded split, openaimodel3d.py:575
+            ctx_text = context[:, :tl].reshape(b * tl, cd)
+            ctx_img = context[:, tl:].reshape(b * t * 16, cd)
+            img_per_frame = True
+        else:
+            ctx_text = context[:, :tl].reshape(b * tl, cd)
+            ctx_img = context[:, tl:].reshape(b * (l_ctx - tl), cd)
+            img_per_frame = False
+        ct = ctx_text.to(torch.bfloat16).contiguous()
+        ci = ctx_img.to(torch.bfloat16).contiguous() if ctx_img.shape[0] else None
+        cache = {"text_len": tl, "img_len": 16 if img_per_frame else (l_ctx - tl),
+                 "img_per_frame": img_per_frame, "kv": {}}
+        inp, mid, out, _ = self.plan
+        for layers in list(inp) + [mid] + list(out):
+            for L in layers:
+                if L[0] != "st":
+                    continue
+                a2 = f"{L[1]}.transformer_blocks.0.attn2"
+                kv_t = ops.linear(ct, P[f"{a2}.kv"])
+                kv_i = ops.linear(ci, P[f"{a2}.kv_ip"]) if (ci is not None and self.image_cross_attention) else None
+                cache["kv"][L[1]] = (kv_t, kv_i)
+        cache["key"] = (context.data_ptr(), context._version, tuple(context.shape), t)
+        self._ctx_cache = cache
+
+    # ------------------------------------------------------------------ blocks
+    def _basic_block(self, x, p, heads, geom, spatial_kv=None):
+        """BasicTransformerBlock._forward (attention.py:242-246) on rows x [M, inner] (in place on x)."""
+        P = self._packed
+        b, t, hh, ww = geom
+        M, inner = x.shape
+        n1 = ops.layernorm(x, P[f"{p}.norm1.g"], P[f"{p}.norm1.be"])
+        qkv = ops.linear(n1, P[f"{p}.attn1.qkv"])
+        o = torch.empty((M, inner), device=x.device, dtype=torch.bfloat16)
+        q, k, v = qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:]
+        if spatial_kv is not None:
+            ops.attention(q, k, v, o, b * t, heads, hh * ww, hh * ww)
+        else:
+            ops.temporal_attention(q, k, v, o, b, t, hh * ww, heads)
+        ops.linear(o, P[f"{p}.attn1.to_out.0.w"], P[f"{p}.attn1.to_out.0.b"], residual=x, out=x)
+        n2 = ops.layernorm(x, P[f"{p}.norm2.g"], P[f"{p}.norm2.be"])
+        if spatial_kv is not None:
+            kv_t, kv_i = spatial_kv
+            cc = self._ctx_cache
+            q2 = ops.linear(n2, P[f"{p}.attn2.q"])
+            ops.attention(q2, kv_t[:, :inner], kv_t[:, inner:], o, b * t, heads, hh * ww, cc["text_len"],
+                          kv_batch_div=t)
+            if kv_i is not None:
+                ops.attention(q2, kv_i[:, :inner], kv_i[:, inner:], o, b * t, heads, hh * ww, cc["img_len"],
+                              kv_batch_div=1 if cc["img_per_frame"] else t, accumulate=True)
+        else:
+            qkv2 = ops.linear(n2, P[f"{p}.attn2.qkv"])
+            ops.temporal_attention(qkv2[:, :inner], qkv2[:, inner:2 * inner], qkv2[:, 2 * inner:], o, b, t,
+                                   hh * ww, heads)
+        ops.linear(o, P[f"{p}.attn2.to_out.0.w"], P[f"{p}.attn2.to_out.0.b"], residual=x, out=x)
+        n3 = ops.layernorm(x, P[f"{p}.norm3.g"], P[f"{p}.norm3.be"])
+        g = ops.linear(n3, P[f"{p}.ff.w1"], P[f"{p}.ff.b1"], act=ops.ACT_GEGLU)
+        ops.linear(g, P[f"{p}.ff.net.2.w"], P[f"{p}.ff.net.2.b"], residual=x, out=x)
+        return x
+
+    def _spatial_transformer(self, h, p, heads, geom):
+        """SpatialTransformer.forward attention.py:294-310 (use_linear)."""
+        P = self._packed
+        b, t, hh, ww = geom
+        a = ops.groupnorm(h, b * t, hh * ww, P[f"{p}.norm.g"], P[f"{p}.norm.be"], 1e-6, False)
+        x = ops.linear(a, P[f"{p}.proj_in.w"], P[f"{p}.proj_in.b"])
+        x = self._basic_block(x, f"{p}.transformer_blocks.0", heads, geom, spatial_kv=self._ctx_cache["kv"][p])
+        return ops.linear(x, P[f"{p}.proj_out.w"], P[f"{p}.proj_out.b"], residual=h)
+
+    def _temporal_transformer(self, h, p, heads, geom):
+        """TemporalTransformer.forward attention.py:365-412 (only_self_att); GroupNorm statistics span
+        (C/32, t, h, w) because the reference normalises the 5-D 'b c t h w' view."""
+        P = self._packed
+        b, t, hh, ww = geom
+        a = ops.groupnorm(h, b, t * hh * ww, P[f"{p}.norm.g"], P[f"{p}.norm.be"], 1e-6, False)
+        x = ops.linear(a, P[f"{p}.proj_in.w"], P[f"{p}.proj_in.b"])
+        x = self._basic_block(x, f"{p}.transformer_blocks.0", heads, geom, spatial_kv=None)
+        return ops.linear(x, P[f"{p}.proj_out.w"], P[f"{p}.proj_out.b"], residual=h)
+
+    def _resblock(self, h, L, emb_all, geom):
+        """ResBlock._forward (openaimodel3d.py:210-236) + TemporalConvBlock (:272-279)."""
+        P = self._packed
+        p, cin, cout, tconv = L[1], L[2], L[3], L[4]
+        b, t, hh, ww = geom
+        nf, hw = b * t, hh * ww
+        off, _ = self._emb_slices[p]
+        a = ops.groupnorm(h, nf, hw, P[f"{p}.in_layers.0.g"], P[f"{p}.in_layers.0.be"], 1e-5, True)
+        h1 = ops.conv3x3(a, nf, hh, ww, P[f"{p}.in_layers.2.w"], P[f"{p}.in_layers.2.b"],
+                         row_bias=emb_all[:, off:off + cout], rows_per_bias=t * hw)
+        a2 = ops.groupnorm(h1, nf, hw, P[f"{p}.out_layers.0.g"], P[f"{p}.out_layers.0.be"], 1e-5, True)
+        skip = h if cin == cout else ops.linear(h, P[f"{p}.skip_connection.w"], P[f"{p}.skip_connection.b"])
+        h2 = ops.conv3x3(a2, nf, hh, ww, P[f"{p}.out_layers.3.w"], P[f"{p}.out_layers.3.b"], residual=skip)
+        if not tconv:
+            return h2
+        x = h2
+        for k in ("conv1", "conv2", "conv3", "conv4"):
+            q = f"{p}.temopral_conv.{k}"
+            a = ops.groupnorm(x, b, t * hw, P[f"{q}.0.g"], P[f"{q}.0.be"], 1e-5, True)
+            x = ops.temporal_conv3(a, b, t, hw, P[f"{q}.w"], P[f"{q}.b"], residual=h2 if k == "conv4" else None)
+        return x
+
+    def _run(self, layers, h, emb_all, geom):
+        P = self._packed
+        b, t, hh, ww = geom
+        for L in layers:
+            kind, p = L[0], L[1]
+            if kind == "conv":
+                h = ops.conv3x3(h, b * t, hh, ww, P[f"{p}.w"], P[f"{p}.b"])
+            elif kind == "res":
+                h = self._resblock(h, L, emb_all, geom)
+            elif kind == "st":
+                h = self._spatial_transformer(h, p, L[3], geom)
+            elif kind == "tt":
+                h = self._temporal_transformer(h, p, L[3], geom)
+            elif kind == "down":
+                ho, wo = (hh + 2 - 3) // 2 + 1, (ww + 2 - 3) // 2 + 1
+                col = ops.im2col_s2(h, b * t, hh, ww, 1, ho, wo)
+                h = ops.linear(col, P[f"{p}.w"], P[f"{p}.b"])
+                hh, ww = ho, wo
+                geom = (b, t, hh, ww)
+            elif kind == "up":
+                u = ops.upsample2x(h, b * t, hh, ww)
+                hh, ww = 2 * hh, 2 * ww
+                geom = (b, t, hh, ww)
+                h = ops.conv3x3(u, b * t, hh, ww, P[f"{p}.w"], P[f"{p}.b"])
+        return h, geom
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward_rows(self, x_rows: torch.Tensor, emb_all: torch.Tensor, geom, taps: Optional[dict] = None):
+        """Core network on rows: x_rows bf16 [(b t h w), Cin_pad] -> fp32 rows [(b t h w), out_channels]."""
+        P = self._packed
+        inp, mid, out, _ = self.plan
+        hs: List = []
+        h = x_rows
+        for i, layers in enumerate(inp):
+            h, geom = self._run(layers, h, emb_all, geom)
+            if i == 0 and self.addition_attention:
+                h = self._temporal_transformer(h, "init_attn.0", self.init_attn_heads, geom)
+            hs.append(h)
+            if taps is not None:
+                taps[f"input_blocks.{i}"] = (h, geom)
+        h, geom = self._run(mid, h, emb_all, geom)
+        if taps is not None:
+            taps["middle_block"] = (h, geom)
+        for i, layers in enumerate(out):
+            h = ops.concat_rows(h, hs.pop())
+            h, geom = self._run(layers, h, emb_all, geom)
+            if taps is not None:
+                taps[f"output_blocks.{i}"] = (h, geom)
+        b, t, hh, ww = geom
+        a = ops.groupnorm(h, b * t, hh * ww, P["out.0.g"], P["out.0.be"], 1e-5, True)
+        return ops.conv3x3(a, b * t, hh, ww, P["out.2.w"], P["out.2.b"], out_dtype=torch.float32)
+
+    @torch.no_grad()
+    def forward(self, x, timesteps, context=None, features_adapter=None, fs=None, task=None, **kwargs):
+        """x [b, in_ch, t, h, w] fp32, timesteps [b], context [b, 77+16t, ctx], fs [b] -> [b, out_ch, t, h, w]."""
+        if features_adapter is not None or task is not None:
+            raise NotImplementedError("features_adapter / task conditioning are not part of the Geo4D path")
+        if self._packed is None:
+            self.prepare()
+        if timesteps.dim() != 1:
+            raise ValueError("per-frame timesteps are not used by the Geo4D inference path")
+        b, _, t, hh, ww = x.shape
+        if context is None:
+            raise ValueError("context is required (conditioning_key='hybrid')")
+        key = (context.data_ptr(), context._version, tuple(context.shape), t)
+        if self._ctx_cache is None or self._ctx_cache["key"] != key:
+            self.set_context(context, t)
+        emb_all = self.embed(timesteps, fs, b)
+        cin_pad = -(-self.in_channels // 64) * 64
+        x_rows = ops.bcthw_to_rows(x.float().contiguous(), None, cin_pad)
+        y_rows = self.forward_rows(x_rows, emb_all, (b, t, hh, ww))
+        return ops.rows_to_bcthw(y_rows, self.out_channels, b, t, hh, ww)

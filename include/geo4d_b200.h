@@ -93,12 +93,13 @@ int geo4d_tap_gemm(const g4_gemm_desc* d, g4_stream_t stream);
  * scores stay in TMEM/registers).  Replaces xformers.ops.memory_efficient_attention as called from
  * CrossAttention.efficient_forward (attention.py:146-209; einsum fallback :101-125).
  *   q   : bf16 [B*Lq rows, ldq]   head h at columns [h*64, h*64+64)
- *   k,v : bf16 [B*Lk rows, ldkv]  (kv_shared: [Lk rows], same keys for every batch entry)
+ *   k,v : bf16 [ceil(B/kv_batch_div)*Lk rows, ldkv]; batch entry b uses K/V block b / kv_batch_div
+ *         (kv_batch_div = frames per clip for the text keys that repeat_interleave shares, 1 otherwise)
  *   out : bf16 [B*Lq rows, ldo];  accumulate != 0 adds to the existing contents (second
  *         cross-attention branch, attention.py:203-207).
  * ---------------------------------------------------------------------------------------------- */
 int geo4d_attention(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* out,
-                    int64_t ldo, int B, int H, int Lq, int Lk, int kv_shared, int accumulate, float scale,
+                    int64_t ldo, int B, int H, int Lq, int Lk, int kv_batch_div, int accumulate, float scale,
                     g4_stream_t stream);
 
 /* Temporal self-attention over <=16 frame tokens per (pixel, head) (CrossAttention.forward
@@ -135,6 +136,13 @@ int geo4d_ddim_step(float* x, const float* v, float* pred_x0, const float* noise
                     const int* step_idx, int64_t n, g4_stream_t stream);
 int geo4d_advance_counter(int* counter, int delta, int modulo, g4_stream_t stream);
 int geo4d_gather_row(const float* table, int64_t ld, const int* idx, float* out, int n, g4_stream_t stream);
+
+/* VAE mid AttnBlock helpers (single head, d = C; ae_modules.py:53-78): row softmax of the fp32 score
+ * matrix to bf16 probabilities, and a batched bf16 transpose out[b, c, r] = in[b, r, c] (to feed V^T as
+ * the K-major B operand of the P V batched matmul). */
+int geo4d_softmax_rows(const float* s, int64_t lds, void* p_bf16, int64_t ldp, int64_t rows, int cols,
+                       g4_stream_t stream);
+int geo4d_transpose_bf16(const void* in, int64_t ldin, void* out, int batch, int R, int C, g4_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -170,8 +170,8 @@ def main():
     rv = ref_vae(vt)
     rv.load_state_dict(vsd, strict=True)
     g = torch.Generator().manual_seed(5)
-    img = torch.randn(2, 3, 32, 64, generator=g)
-    z = torch.randn(2, 4, 4, 8, generator=g)
+    img = torch.randn(2, 3, 64, 64, generator=g)
+    z = torch.randn(2, 4, 8, 8, generator=g)
     with torch.no_grad():
         mom_ref = rv.quant_conv(rv.encoder(img))
         dec_ref = rv.decoder(rv.post_quant_conv(z))

@@ -162,7 +162,7 @@ def _attn_case(B, H, Lq, Lk, kv_shared=False, accumulate=False, seed=0):
     kv = torch.randn(Bk * Lk, 2 * inner, device="cuda", generator=g).bfloat16()
     out = torch.randn(B * Lq, inner, device="cuda", generator=g).bfloat16() if accumulate else torch.empty(B * Lq, inner, device="cuda", dtype=torch.bfloat16)
     prev = out.float().clone()
-    ops.attention(q, kv[:, :inner], kv[:, inner:], out, B, H, Lq, Lk, kv_shared=kv_shared, accumulate=accumulate)
+    ops.attention(q, kv[:, :inner], kv[:, inner:], out, B, H, Lq, Lk, kv_batch_div=(B if kv_shared else 1), accumulate=accumulate)
     torch.cuda.synchronize()
     k = kv[:, :inner].reshape(Bk, Lk, inner); v = kv[:, inner:].reshape(Bk, Lk, inner)
     if kv_shared: k = k.expand(B, Lk, inner); v = v.expand(B, Lk, inner)
