@@ -186,7 +186,7 @@ def main():
     assert max(e_enc, e_dec, e_conf) < 1e-5, report["vae_tiny_rel_l2"]
     torch.save({"img": img, "z": z, "moments": mom_ref, "dec": dec_ref,
                 "dec_conf": torch.cat([rgb_ref, conf_ref], 1), "seed": 3,
-                "cfg": dict(ch=32, adaptor_ch=32)}, os.path.join(GOLD, "vae_tiny.pt"))
+                "cfg": dict(ch=64, adaptor_ch=64)}, os.path.join(GOLD, "vae_tiny.pt"))
 
     # ------------------------------------------------------------------ schedule + DDIM
     from lvdm.models.utils_diffusion import (make_beta_schedule, rescale_zero_terminal_snr,

@@ -39,7 +39,7 @@ class VAEConfig:
 
     @staticmethod
     def tiny(**kw) -> "VAEConfig":
-        base = dict(ch=32, adaptor_ch=32)
+        base = dict(ch=64, adaptor_ch=64)
         base.update(kw)
         return VAEConfig(**base)
 
