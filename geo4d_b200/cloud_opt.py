@@ -1,0 +1,648 @@
+"""Sliding-window global alignment behind the reference's `LightPointCloudGroupOptimizer` seam
+(dust3r/cloud_opt/optimizer_group.py + base_opt_group.py + init_im_poses.py, group path).
+
+Same constructor arguments, `compute_global_alignment(init='group', niter, schedule, lr)` and getters
+(`get_depthmaps`, `get_im_poses`, `get_focals`, `get_intrinsics`, `get_pts3d`, `get_tum_poses`, `get_masks`,
+`save_*`) as the reference.  What runs where:
+
+* dense work -- the per-pixel objective, its gradient w.r.t. every log-depth value, the Adam update of
+  the N x HW log-depth maps and the reductions of the gradient w.r.t. poses / focal / window sim(3) /
+  depth scale-shift -- is ONE fused kernel per iteration (geo4d_align_iter); the weighted Umeyama
+  registrations, the LAD scale/shift fit (same Adam iteration as the reference, batched over windows and
+  sync-free) and the delta<1.25 gate are reduction kernels (csrc/align.cu);
+* the O(N + G) small-parameter chain rule (quaternion / signed-log / log-scale parametrisations, the two
+  pose-graph terms) stays in torch autograd on tensors of a few hundred floats, driven by the matrix-form
+  gradients the kernel reduces, and the whole iteration is replayed from a CUDA graph (two graphs:
+  before / after `depth_traj_start_iter`);
+* like the reference, the shift/focal Levenberg-Marquardt solve (scipy) and the per-frame RANSAC-PnP (cv2)
+  of the initialisation run on the host (SURVEY.md 8(f) N2 ports them next).
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._cabi import require_device
+
+
+# --------------------------------------------------------------------------- small helpers (host / torch)
+def signed_log1p(x):
+    return torch.sign(x) * torch.log1p(torch.abs(x))
+
+
+def signed_expm1(x):
+    return torch.sign(x) * torch.expm1(torch.abs(x))
+
+
+def unitquat_to_rotmat(q):
+    """xyzw (roma convention, base_opt_group.py:264,279)."""
+    x, y, z, w = q.unbind(-1)
+    R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                     2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                     2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], -1)
+    return R.reshape(*q.shape[:-1], 3, 3)
+
+
+def rotmat_to_unitquat_np(m: np.ndarray) -> np.ndarray:
+    d = np.array([m[0, 0], m[1, 1], m[2, 2], m[0, 0] + m[1, 1] + m[2, 2]])
+    k = int(np.argmax(d))
+    q = np.empty(4)
+    if k == 3:
+        q[:] = (m[2, 1] - m[1, 2], m[0, 2] - m[2, 0], m[1, 0] - m[0, 1], 1 + d[3])
+    else:
+        i, j, l = k, (k + 1) % 3, (k + 2) % 3
+        q[i] = 1 - d[3] + 2 * m[i, i]
+        q[j] = m[j, i] + m[i, j]
+        q[l] = m[l, i] + m[i, l]
+        q[3] = m[l, j] - m[j, l]
+    return q / np.linalg.norm(q)
+
+
+def poses_from_params(p):
+    """_get_poses (base_opt_group.py:260-265) -> [n, 4, 4] cam-to-world."""
+    q = p[:, :4]
+    q = q / q.norm(dim=-1, keepdim=True)
+    R = unitquat_to_rotmat(q)
+    T = signed_expm1(p[:, 4:7])
+    top = torch.cat([R, T.unsqueeze(-1)], -1)
+    bot = torch.zeros(p.shape[0], 1, 4, device=p.device, dtype=p.dtype)
+    bot[:, 0, 3] = 1
+    return torch.cat([top, bot], 1)
+
+
+def umeyama_from_moments(m0: np.ndarray, m1: np.ndarray):
+    """(sum w, sum w x, sum w y) and (sum w|x^|^2, sum w y^ x^T) -> (s, R, T) with y ~ s R x + T."""
+    sw = m0[0]
+    xm, ym = m0[1:4] / sw, m0[4:7] / sw
+    M = m1[1:10].reshape(3, 3)
+    U, D, Vt = np.linalg.svd(M)
+    det = np.linalg.det(U) * np.linalg.det(Vt)
+    Dm = np.array([1.0, 1.0, det])
+    R = U @ np.diag(Dm) @ Vt
+    s = float((D * Dm).sum() / m1[0])
+    T = ym - s * (R @ xm)
+    return s, R, T
+
+
+def _se3_inv(T):
+    R, t = T[:3, :3], T[:3, 3]
+    out = np.eye(4)
+    out[:3, :3] = R.T
+    out[:3, 3] = -R.T @ t
+    return out
+
+
+def c2w_to_tumpose(c2w: np.ndarray) -> np.ndarray:
+    """base_opt_group.py:28-41: xyz + quaternion wxyz."""
+    from scipy.spatial.transform import Rotation
+    qx, qy, qz, qw = Rotation.from_matrix(c2w[:3, :3]).as_quat()
+    return np.concatenate([c2w[:3, -1], [qw, qx, qy, qz]])
+
+
+class LightPointCloudGroupOptimizer(nn.Module):
+    POSE_DIM = 7
+
+    def __init__(self, view_list, pred_list, dist="l1", conf="log", min_conf_thr=3, thr_for_init_conf=False,
+                 base_scale=0.5, allow_pw_adaptors=False, pw_break=20, rand_pose=torch.randn, empty_cache=False,
+                 verbose=True, opt_raydir=False, optimize_pp=False, focal_break=20, shared_focal=False,
+                 flow_loss_fn="smooth_l1", flow_loss_weight=0.0, depth_regularize_weight=0.0, num_total_iter=300,
+                 temporal_smoothing_weight=0, translation_weight=0.1, flow_loss_start_epoch=0.15, flow_loss_thre=50,
+                 sintel_ckpt=False, use_self_mask=False, pxl_thre=50, sam2_mask_refine=True, motion_mask_thre=0.35,
+                 conf_optimize=False, depth_traj_start_iter=150, use_cuda_graph=True, lad_max_iters=5000):
+        super().__init__()
+        if dist != "l1" or conf not in ("id", "none") or not shared_focal or not conf_optimize or opt_raydir \
+                or optimize_pp or allow_pw_adaptors or flow_loss_weight != 0.0 or depth_regularize_weight != 0.0:
+            raise NotImplementedError(
+                "geo4d_b200 implements the configuration the Geo4D scripts use (infer_geo4d.py:32-40): dist='l1', "
+                "conf='id', conf_optimize=True, shared_focal=True, no flow / raydir / pp / adaptor terms")
+        self.groups = [[int(v["idx"][-1]) for v in views] for views in view_list]
+        self.n_groups = len(self.groups)
+        self.group_size = len(self.groups[0])
+        self.n_imgs = max(max(g) for g in self.groups) + 1
+        p0 = pred_list[0]["pts3d"]
+        self.H, self.W = int(p0.shape[1]), int(p0.shape[2])
+        self.HW = self.H * self.W
+        self.imshapes = [(self.H, self.W)] * self.n_imgs
+        self.imshape = (self.H, self.W)
+        self.verbose = verbose
+        self.base_scale = base_scale
+        self.focal_break = focal_break
+        self.shared_focal = shared_focal
+        self.num_total_iter = num_total_iter
+        self.temporal_smoothing_weight = temporal_smoothing_weight
+        self.translation_weight = translation_weight
+        self.depth_traj_start_iter = depth_traj_start_iter
+        self.min_conf_thr = min_conf_thr
+        self.thr_for_init_conf = thr_for_init_conf
+        self.has_im_poses = True
+        self.use_cuda_graph = use_cuda_graph and os.environ.get("GEO4D_ALIGN_EAGER", "0") != "1"
+        self.lad_max_iters = lad_max_iters
+        dev = p0.device
+        G, gs, N, HW = self.n_groups, self.group_size, self.n_imgs, self.HW
+        f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32)
+        # stacked per-(window, frame) observations (optimizer_group.py:91-104)
+        self.register_buffer("_stacked_pred_all", torch.stack([f32(p["pts3d"]).reshape(gs, HW, 3) for p in pred_list])
+                             .reshape(G * gs, HW, 3).contiguous())
+        self.register_buffer("_weight_all", torch.stack([f32(p["conf"]).reshape(gs, HW) for p in pred_list])
+                             .reshape(G * gs, HW).contiguous())
+        self.has_invdepth = pred_list[0].get("inverse_depthmap", None) is not None
+        self.has_traj = pred_list[0].get("traj", None) is not None
+        if self.has_invdepth:
+            self.register_buffer("_stacked_depthmap_all", torch.stack(
+                [f32(p["inverse_depthmap"]).reshape(gs, HW) for p in pred_list]).reshape(G * gs, HW).contiguous())
+        if self.has_traj:
+            self.register_buffer("_stacked_traj_all", torch.stack([f32(p["traj"]) for p in pred_list])
+                                 .reshape(G * gs, 4, 4).contiguous())
+        e_all = [j for g in self.groups for j in g]
+        self.register_buffer("_e_all", torch.tensor(e_all, device=dev))
+        # images -> incident edges (CSR) for the fused kernel
+        inc: List[List[int]] = [[] for _ in range(N)]
+        for e, n in enumerate(e_all):
+            inc[n].append(e)
+        self.max_edges_per_image = max(len(x) for x in inc)
+        ptr = np.zeros(N + 1, dtype=np.int32)
+        ptr[1:] = np.cumsum([len(x) for x in inc])
+        self.register_buffer("_edge_ptr", torch.tensor(ptr, device=dev))
+        self.register_buffer("_edge_idx", torch.tensor([e for x in inc for e in x], dtype=torch.int32, device=dev))
+        self.total_area_all = G * gs * HW
+        # single-image confidence = max over windows (base_opt_group.py:229-235)
+        im_conf = torch.zeros(N, HW, device=dev)
+        for e, n in enumerate(e_all):
+            im_conf[n] = torch.maximum(im_conf[n], self._weight_all[e])
+        self.im_conf = [c.reshape(self.H, self.W) for c in im_conf]
+        self.init_conf_maps = [c.clone() for c in self.im_conf]
+        # parameters.  The reference draws torch.randn initial values that init_from_group / _set_traj fully
+        # overwrite before first use; zeros keep the run deterministic.
+        self.im_depthmaps = nn.Parameter(torch.zeros(N, HW, device=dev), requires_grad=False)  # log-depth
+        self.im_poses = nn.Parameter(torch.zeros(N, self.POSE_DIM, device=dev))
+        self.im_focals = nn.Parameter(torch.full((1, 1), focal_break * math.log(max(self.H, self.W)), device=dev))
+        self.pw_poses = nn.Parameter(torch.zeros(G, 1 + self.POSE_DIM, device=dev))
+        self.traj_align_poses = nn.Parameter(torch.zeros(G, 1 + self.POSE_DIM, device=dev))
+        self.s_depth = nn.Parameter(torch.ones(G, 1, device=dev))
+        self.t_depth = nn.Parameter(torch.zeros(G, 1, device=dev))
+        with torch.no_grad():
+            self.im_poses[:, 3] = 1
+            self.pw_poses[:, 3] = 1
+            self.traj_align_poses[:, 3] = 1
+        self.register_buffer("_pp", torch.tensor([(self.W / 2, self.H / 2)] * N, device=dev))
+        self.invalid_depth_group: List[int] = []
+        self.valid_traj_group_list: List[int] = []
+        self.valid_group_idx: List[int] = []
+        self.imgs = None
+        if "img" in view_list[0][0]:
+            imgs = [None] * N
+            for views in view_list:
+                for v in views:
+                    im = v["img"][0] if v["img"].dim() == 4 else v["img"]
+                    imgs[int(v["idx"][-1])] = (im.detach().float().cpu().permute(1, 2, 0).numpy() * 0.5 + 0.5)
+            self.imgs = imgs
+
+    @property
+    def device(self):
+        return self.im_poses.device
+
+    # ------------------------------------------------------------------ getters (reference names)
+    def get_focals(self):
+        lf = torch.stack([self.im_focals[0]] * self.n_imgs, dim=0)
+        return (lf / self.focal_break).exp()
+
+    def get_principal_points(self):
+        return self._pp
+
+    def get_intrinsics(self):
+        K = torch.zeros((self.n_imgs, 3, 3), device=self.device)
+        f = self.get_focals().flatten()
+        K[:, 0, 0] = K[:, 1, 1] = f
+        K[:, :2, 2] = self.get_principal_points()
+        K[:, 2, 2] = 1
+        return K
+
+    def get_im_poses(self):
+        return poses_from_params(self.im_poses)
+
+    def get_pw_norm_scale_factor(self):
+        return (math.log(self.base_scale) - self.pw_poses[:, -1].mean()).exp()
+
+    def get_pw_scale(self):
+        return self.pw_poses[:, -1].exp() * self.get_pw_norm_scale_factor()
+
+    def get_pw_poses(self):
+        RT = poses_from_params(self.pw_poses)
+        sc = self.get_pw_scale().view(-1, 1, 1)
+        return torch.cat([RT[:, :3] * sc, RT[:, 3:]], 1)
+
+    def get_depthmaps(self, raw=False):
+        res = self.im_depthmaps.detach().exp()
+        if not raw:
+            res = [dm.view(self.H, self.W) for dm in res]
+        return res
+
+    def get_pts3d(self, raw=False, **kw):
+        with torch.no_grad():
+            depth = self.im_depthmaps.exp().unsqueeze(-1)
+            ys, xs = torch.meshgrid(torch.arange(self.H, device=self.device),
+                                    torch.arange(self.W, device=self.device), indexing="ij")
+            grid = torch.stack([xs, ys], -1).reshape(1, self.HW, 2).float()
+            f = self.get_focals().unsqueeze(1)
+            rel = torch.cat((depth * (grid - self._pp.unsqueeze(1)) / f, depth), dim=-1)
+            P = self.get_im_poses()
+            res = torch.einsum("nij,npj->npi", P[:, :3, :3], rel) + P[:, None, :3, 3]
+        if not raw:
+            res = [r.view(self.H, self.W, 3) for r in res]
+        return res
+
+    def get_masks(self):
+        confs = self.init_conf_maps if self.thr_for_init_conf else self.im_conf
+        return [(c > self.min_conf_thr) for c in confs]
+
+    def get_conf(self, mode=None):
+        return list(self.im_conf)
+
+    def get_tum_poses(self):
+        poses = self.get_im_poses().detach().cpu().numpy()
+        return [np.stack([c2w_to_tumpose(p) for p in poses], 0), np.arange(len(poses)).astype(float)]
+
+    def save_tum_poses(self, path):
+        traj, tt = self.get_tum_poses()
+        with open(path, "w") as f:  # vo_eval.py:465-473 (TUM: timestamp tx ty tz qx qy qz qw)
+            for i in range(len(tt)):
+                p = traj[i]
+                f.write(f"{tt[i]} {p[0]} {p[1]} {p[2]} {p[4]} {p[5]} {p[6]} {p[3]}\n")
+        return traj
+
+    def save_focals(self, path):
+        focals = self.get_focals()
+        np.savetxt(path, focals.detach().cpu().numpy(), fmt="%.6f")
+        return focals
+
+    def save_intrinsics(self, path):
+        K = self.get_intrinsics().detach().cpu().numpy()
+        np.savetxt(path, K.reshape(-1, 9), fmt="%.6f")
+        return K
+
+    def save_depth_maps(self, path):
+        dms = self.get_depthmaps()
+        for i, d in enumerate(dms):
+            np.save(f"{path}/frame_{i:04d}.npy", d.detach().cpu().numpy())
+        return dms
+
+    def save_conf_maps(self, path):
+        for i, c in enumerate(self.im_conf):
+            np.save(f"{path}/conf_{i}.npy", c.detach().cpu().numpy())
+        return self.im_conf
+
+    def save_init_conf_maps(self, path):
+        for i, c in enumerate(self.init_conf_maps):
+            np.save(f"{path}/init_conf_{i}.npy", c.detach().cpu().numpy())
+        return self.init_conf_maps
+
+    def preset_focal(self, known_focals, msk=None, requires_grad=False):
+        with torch.no_grad():
+            self.im_focals[:] = self.focal_break * math.log(float(sum(float(f) for f in known_focals) /
+                                                                  len(known_focals)))
+        if len(known_focals) == self.n_imgs:
+            self.im_focals.requires_grad_(requires_grad)
+
+    # ------------------------------------------------------------------ init (init_from_group)
+    def _umeyama(self, x, y, w1, w2):
+        """weighted Umeyama y ~ s R x + T on the GPU reduction kernel; x, y [n,3], w1, w2 [n]."""
+        n = x.shape[0]
+        m0 = ops.umeyama_moments(x, y, w1, w2, n, 0, None)
+        means = (m0[1:7] / m0[0]).contiguous()
+        m1 = ops.umeyama_moments(x, y, w1, w2, n, 1, means)
+        return umeyama_from_moments(m0.cpu().numpy(), m1.cpu().numpy())
+
+    @staticmethod
+    def _set_pose(poses, idx, R, T, scale=None, scale_T=True):
+        with torch.no_grad():
+            poses[idx, 0:4] = torch.as_tensor(rotmat_to_unitquat_np(np.asarray(R, dtype=np.float64)),
+                                              dtype=poses.dtype, device=poses.device)
+            Tt = torch.as_tensor(np.asarray(T, dtype=np.float64), dtype=poses.dtype, device=poses.device)
+            poses[idx, 4:7] = signed_log1p(Tt / (scale if (scale is not None and scale_T) else 1))
+            if scale is not None:
+                poses[idx, -1] = math.log(float(scale))
+
+    @torch.no_grad()
+    def _init_from_group(self, niter_PnP=10):
+        from . import init_solvers as isv
+        G, gs, N, HW, H, W = self.n_groups, self.group_size, self.n_imgs, self.HW, self.H, self.W
+        dev = self.device
+        pred = self._stacked_pred_all.view(G, gs, HW, 3)
+        conf = self._weight_all.view(G, gs, HW)
+        focal_group = isv.focal_per_group(pred[:, 0].reshape(G, H, W, 3).cpu(), conf[:, 0].reshape(G, H, W).cpu())
+        pts3d = torch.zeros(N, HW, 3, device=dev)
+        conf_list = torch.zeros(N, HW, device=dev)
+        im_poses: List[Optional[np.ndarray]] = [None] * N
+        im_focals: List[Optional[float]] = [None] * N
+        done = set()
+
+        def pnp_frames(frame_ids, pts_cpu, msk_cpu, first_focal_of):
+            for k, img in enumerate(frame_ids):
+                tf = first_focal_of(k, img)
+                res = isv.fast_pnp(pts_cpu[k], tf, msk_cpu[k], niter_PnP)
+                if res:
+                    im_focals[img], im_poses[img] = res
+                if im_poses[img] is None:
+                    im_poses[img] = np.eye(4)
+
+        g0 = self.groups[0]
+        im_focals[g0[0]] = focal_group[0]
+        pts3d[g0] = pred[0]
+        conf_list[g0] = conf[0]
+        pnp_frames(g0, pred[0].reshape(gs, H, W, 3).cpu().numpy(), (conf[0] > 0.5).reshape(gs, H, W).cpu().numpy(),
+                   lambda k, img: im_focals[img - 1] if img != 0 else im_focals[img])
+        done.update(g0)
+        for i in range(1, G):
+            group = self.groups[i]
+            assert group[0] in done, "The first image of the following group should be in the previous group"
+            seen = [(k, img) for k, img in enumerate(group) if img in done]
+            ks = torch.tensor([k for k, _ in seen], device=dev)
+            ims = torch.tensor([img for _, img in seen], device=dev)
+            s, R, T = self._umeyama(pred[i][ks].reshape(-1, 3).contiguous(), pts3d[ims].reshape(-1, 3).contiguous(),
+                                    conf[i][ks].reshape(-1).contiguous(), conf_list[ims].reshape(-1).contiguous())
+            sR = torch.tensor(s * R, device=dev, dtype=torch.float32)
+            Tt = torch.tensor(T, device=dev, dtype=torch.float32)
+            new_pts = pred[i] @ sR.T + Tt
+            pts3d[group] = new_pts
+            conf_list[group] = conf[i]
+            if im_poses[group[0]] is None:
+                P = np.eye(4)
+                P[:3, :3], P[:3, 3] = R, T
+                im_poses[group[0]] = P
+            pnp_frames(group, new_pts.reshape(gs, H, W, 3).cpu().numpy(),
+                       (conf[i] > 0.5).reshape(gs, H, W).cpu().numpy(),
+                       lambda k, img, fg=focal_group[i]: fg if k == 0 else im_focals[img - 1])
+            done.update(group)
+        im_poses_np = np.stack(im_poses)
+        # init_from_pts3d_group (init_im_poses.py:569-633)
+        for e, group in enumerate(self.groups):
+            gi = torch.tensor(group, device=dev)
+            s, R, T = self._umeyama(pred[e].reshape(-1, 3).contiguous(), pts3d[gi].reshape(-1, 3).contiguous(),
+                                    conf[e].reshape(-1).contiguous(), conf_list[gi].reshape(-1).contiguous())
+            self._set_pose(self.pw_poses, e, R, T, scale=s)
+        s_factor = float(self.get_pw_norm_scale_factor())
+        im_poses_np[:, :3, 3] *= s_factor
+        pts3d *= s_factor
+        w2c = torch.tensor(np.linalg.inv(im_poses_np), device=dev, dtype=torch.float32)
+        depth = torch.einsum("nj,npj->np", w2c[:, 2, :3], pts3d) + w2c[:, 2, 3:4]
+        sky = conf_list < 1e-4
+        sky_distance = depth[0].max()
+        depth = torch.where(sky, sky_distance.expand_as(depth), depth)
+        self.im_depthmaps.data.copy_(depth.log().nan_to_num(neginf=0))
+        for i in range(N):
+            self._set_pose(self.im_poses, i, im_poses_np[i][:3, :3], im_poses_np[i][:3, 3])
+        self.im_focals.data[:] = self.focal_break * math.log(sum(im_focals) / N)
+        self._init_im_focals = im_focals
+
+    # ------------------------------------------------------------------ iteration-150 sub-alignments
+    @torch.no_grad()
+    def _set_st_depth(self):
+        """optimizer_group.py:333-372 with the LAD fit of depth_eval.py:112-145 on the GPU."""
+        G, n = self.n_groups, self.group_size * self.HW
+        dev = self.device
+        y = (1.0 / (self.im_depthmaps.exp() + 1e-6))[self._e_all].reshape(G, n).contiguous()
+        x = self._stacked_depthmap_all.reshape(G, n)
+        w = self._weight_all.reshape(G, n)
+        s_init = torch.median(y, dim=1).values / torch.median(x, dim=1).values
+
+        def fit(lr, iters):
+            state = torch.zeros(G, 9, device=dev)
+            state[:, 0] = s_init
+            acc = torch.zeros(G * 3, device=dev, dtype=torch.float64)
+            chunk = 250
+            graph = None
+            done_iters = 0
+            if self.use_cuda_graph and iters >= 2 * chunk:
+                ops.lad_step(x, y, n, G, state, acc, lr)  # warm-up (real iteration 0)
+                done_iters = 1
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                n0 = ops.raw_launch_count()
+                with torch.cuda.stream(side), torch.cuda.graph(graph, stream=side):
+                    for _ in range(chunk):
+                        ops.lad_step(x, y, n, G, state, acc, lr)
+                torch.cuda.current_stream().wait_stream(side)
+                nk = ops.raw_launch_count() - n0
+                ops.note_replay(nk, -1)
+                while done_iters + chunk <= iters:
+                    graph.replay()
+                    ops.note_replay(nk)
+                    done_iters += chunk
+            for _ in range(iters - done_iters):
+                ops.lad_step(x, y, n, G, state, acc, lr)
+            d = ops.delta125(x, y, w, n, G, state, 9).cpu().numpy()
+            d1 = np.where(d[:, 1] > 0, d[:, 0] / np.maximum(d[:, 1], 1), 0.0)
+            return state[:, :2].clone(), d1
+
+        best_st, best_d1 = fit(1e-2, self.lad_max_iters)
+        retry = best_d1 < 0.8
+        if retry.any():
+            for lr in (1e-4, 1e-3):
+                st, d1 = fit(lr, min(3000, self.lad_max_iters))
+                better = retry & (d1 > best_d1)
+                bt = torch.tensor(better, device=dev)
+                best_st = torch.where(bt[:, None], st, best_st)
+                best_d1 = np.where(better, d1, best_d1)
+        self.s_depth.data[:, 0] = best_st[:, 0]
+        self.t_depth.data[:, 0] = best_st[:, 1]
+        return [int(i) for i in np.nonzero(best_d1 < 0.3)[0]]
+
+    @torch.no_grad()
+    def _set_traj(self):
+        """optimizer_group.py:242-267; evo align_origin + RPE-rot gate restated."""
+        im_pose = self.get_im_poses().double().cpu().numpy()
+        pw_scale = self.get_pw_scale().double().cpu().numpy()
+        traj_all = self._stacked_traj_all.view(self.n_groups, self.group_size, 4, 4).double().cpu().numpy()
+        valid, valid_idx = [], []
+        for i in range(self.n_groups):
+            group = self.groups[i]
+            traj = traj_all[i].copy()
+            traj[:, :3, 3] *= pw_scale[i]
+            ref = im_pose[group]
+            P = ref[0] @ _se3_inv(traj[0])
+            ang = []
+            for k in range(len(group) - 1):
+                q_rel = _se3_inv(ref[k]) @ ref[k + 1]
+                p_rel = _se3_inv(traj[k]) @ traj[k + 1]
+                E = _se3_inv(q_rel) @ p_rel
+                ang.append(np.degrees(np.arccos(np.clip((np.trace(E[:3, :3]) - 1) / 2, -1, 1))))
+            rpe_rot = float(np.sqrt(np.mean(np.square(ang)))) if ang else 0.0
+            self._set_pose(self.traj_align_poses, i, P[:3, :3], P[:3, 3], scale=float(pw_scale[i]), scale_T=False)
+            if rpe_rot < 4:
+                valid.append(i)
+                valid_idx += group
+        return valid, valid_idx
+
+    # ------------------------------------------------------------------ one optimisation step
+    @staticmethod
+    def _rigid_inverse(RT):
+        """inverse of [R T; 0 1] = [R^T, -R^T T; 0 1] (the reference calls torch.inverse on rigid matrices;
+        the closed form is CUDA-graph capturable and sync-free)."""
+        Rt = RT[:, :3, :3].transpose(1, 2)
+        t = -torch.matmul(Rt, RT[:, :3, 3:4])
+        return torch.cat([torch.cat([Rt, t], -1), RT[:, 3:4, :]], 1)
+
+    def relative_pose_loss(self, RT1, RT2):
+        rel = torch.matmul(self._rigid_inverse(RT1), RT2)
+        rot = torch.norm(rel[:, :3, :3] - torch.eye(3, device=RT1.device), dim=(1, 2))
+        tr = torch.norm(rel[:, :3, 3], dim=1)
+        return rot + tr * self.translation_weight
+
+    def _iteration(self, st: dict, phase_b: bool):
+        N, G, HW = self.n_imgs, self.n_groups, self.HW
+        for opt in st["opts"] if phase_b else st["opts"][:1]:
+            opt.zero_grad(set_to_none=True)
+        lr_now = st["lr_table"].index_select(0, st["it"].long())
+        st["lr_a"].copy_(lr_now.reshape(()))
+        if phase_b:
+            st["lr_b"].copy_(lr_now.reshape(()))
+        P = self.get_im_poses()
+        Pw = self.get_pw_poses()
+        invf = (-self.im_focals / self.focal_break).exp()
+        with torch.no_grad():
+            st["poses"].copy_(P[:, :3, :].reshape(N, 12))
+            st["S"].copy_(Pw[:, :3, :].reshape(G, 12))
+            st["invf"].copy_(invf.reshape(1))
+            if phase_b:
+                st["st"][:, 0].copy_(self.s_depth[:, 0])
+                st["st"][:, 1].copy_(self.t_depth[:, 0])
+        ops.check(ops.lib().geo4d_align_iter(
+            ops._vp(self.im_depthmaps), ops._vp(st["m"]), ops._vp(st["v"]), ops._vp(self._stacked_pred_all),
+            ops._vp(self._weight_all), ops._vp(self._stacked_depthmap_all if self.has_invdepth else None),
+            ops._vp(self._edge_ptr), ops._vp(self._edge_idx), ops._vp(st["poses"]), ops._vp(st["S"]),
+            ops._vp(st["scal"]), ops._vp(st["invf"]), ops._vp(st["it"]), ops._vp(st["st"]), ops._vp(st["gpose"]),
+            ops._vp(st["gS"]), ops._vp(st["gscal"]), ops._vp(st["gst"]), N, G, HW, self.W, self.group_size,
+            self.max_edges_per_image, ops._s()), "geo4d_align_iter")
+        # surrogate whose gradient w.r.t. the small parameters equals that of the dense objective
+        sur = (st["gpose"].float().view(N, 3, 4) * P[:, :3, :]).sum() + \
+              (st["gS"].float().view(G, 3, 4) * Pw[:, :3, :]).sum() + st["gscal"][0].float() * invf.sum()
+        if phase_b and self.has_invdepth:
+            gst = st["gst"].float().view(G, 2)
+            sur = sur + (gst[:, 0] * self.s_depth[:, 0]).sum() + (gst[:, 1] * self.t_depth[:, 0]).sum()
+        if phase_b and self.has_traj and len(self.valid_traj_group_list) > 0:
+            vg = st["valid_groups"]
+            scale = self.traj_align_poses[:, -1].exp()[vg]
+            RT = poses_from_params(self.traj_align_poses)[vg]
+            tr = self._stacked_traj_all.view(G, self.group_size, 4, 4)[vg]
+            xyz = tr[:, :, :3, 3:4] * scale.reshape(-1, 1, 1, 1)
+            top = torch.cat([tr[:, :, :3, :3], xyz], -1)
+            homo = torch.cat([top, tr[:, :, 3:4, :]], -2)
+            homo = torch.matmul(RT.unsqueeze(1), homo).reshape(-1, 4, 4)
+            sur = sur + 0.005 * self.relative_pose_loss(homo, P[st["valid_idx"]]).sum()
+        if self.temporal_smoothing_weight > 0 and N > 1:
+            sur = sur + self.temporal_smoothing_weight * self.relative_pose_loss(P[:-1], P[1:]).sum()
+        sur.backward()
+        st["opts"][0].step()
+        if phase_b:
+            st["opts"][1].step()
+        ops.advance_counter(st["it"], 1)
+
+    def _run_phase(self, st, it0, it1, phase_b):
+        """iterations [it0, it1): a few eager ones (they also serve as the graph warm-up), then replays."""
+        it = it0
+        n_eager = 3 if self.use_cuda_graph else (it1 - it0)
+        while it < it1 and n_eager > 0:
+            self._iteration(st, phase_b)
+            it += 1
+            n_eager -= 1
+        if it >= it1:
+            return
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        n0 = ops.raw_launch_count()
+        with torch.cuda.stream(side), torch.cuda.graph(graph, stream=side):
+            self._iteration(st, phase_b)
+        torch.cuda.current_stream().wait_stream(side)
+        nk = ops.raw_launch_count() - n0
+        ops.note_replay(nk, -1)
+        for _ in range(it, it1):
+            graph.replay()
+        ops.note_replay(nk, it1 - it)
+
+    @torch.no_grad()
+    def _current_loss(self, st, phase_b) -> float:
+        """Objective value at the current parameters (optimizer_group.py:523), from the kernel's reductions."""
+        li = float(st["gscal"][1]) / self.total_area_all
+        dl = 2.0 * float(st["gscal"][2]) / self.total_area_all if phase_b else 0.0
+        return li + dl
+
+    # ------------------------------------------------------------------ public entry point
+    def compute_global_alignment(self, init=None, save_score_path=None, save_score_only=False, niter_PnP=10,
+                                 lr=0.01, niter=300, schedule="cosine", lr_min=1e-3, **kw):
+        require_device()
+        if init == "group":
+            self._init_from_group(niter_PnP=niter_PnP)
+        elif init is not None:
+            raise NotImplementedError(f"init={init!r}: only the 'group' initialisation is used by Geo4D")
+        return self._global_alignment_loop(lr=lr, niter=niter, schedule=schedule, lr_min=lr_min)
+
+    def _global_alignment_loop(self, lr, niter, schedule, lr_min):
+        dev = self.device
+        N, G = self.n_imgs, self.n_groups
+        tt = np.arange(niter) / niter
+        if schedule == "linear":
+            lrs = lr + (lr_min - lr) * tt
+        elif schedule == "cosine":
+            lrs = lr_min + (lr - lr_min) * (1 + np.cos(tt * np.pi)) / 2
+        else:
+            raise ValueError(f"bad lr schedule={schedule!r}")
+        start_b = self.depth_traj_start_iter if (self.has_invdepth or self.has_traj) else niter
+        scal = np.zeros((niter, 8), dtype=np.float32)
+        steps = np.arange(1, niter + 1, dtype=np.float64)
+        scal[:, 1], scal[:, 2] = self.W / 2, self.H / 2
+        scal[:, 3] = lrs
+        scal[:, 4] = 1.0 - 0.9 ** steps
+        scal[:, 5] = np.sqrt(1.0 - 0.9 ** steps)
+        scal[:, 6] = 1.0 / self.total_area_all
+        scal[start_b:, 7] = 1.0
+        lr_a = torch.tensor(float(lrs[0]), device=dev)
+        lr_b = torch.tensor(float(lrs[0]), device=dev)
+        opt_a = torch.optim.Adam([self.im_poses, self.im_focals, self.pw_poses], lr=lr_a, betas=(0.9, 0.9),
+                                 capturable=True, foreach=True)
+        opt_b = torch.optim.Adam([self.s_depth, self.t_depth, self.traj_align_poses], lr=lr_b, betas=(0.9, 0.9),
+                                 capturable=True, foreach=True)
+        st = {
+            "opts": [opt_a, opt_b], "lr_a": lr_a, "lr_b": lr_b,
+            "lr_table": torch.tensor(lrs, device=dev, dtype=torch.float32),
+            "scal": torch.tensor(scal, device=dev), "it": torch.zeros(1, device=dev, dtype=torch.int32),
+            "m": torch.zeros(N, self.HW, device=dev), "v": torch.zeros(N, self.HW, device=dev),
+            "poses": torch.zeros(N, 12, device=dev), "S": torch.zeros(G, 12, device=dev),
+            "invf": torch.zeros(1, device=dev), "st": torch.ones(G, 3, device=dev),
+            "gpose": torch.zeros(N, 12, device=dev, dtype=torch.float64),
+            "gS": torch.zeros(G, 12, device=dev, dtype=torch.float64),
+            "gscal": torch.zeros(3, device=dev, dtype=torch.float64),
+            "gst": torch.zeros(G, 2, device=dev, dtype=torch.float64),
+        }
+        opt_a.param_groups[0]["lr"] = lr_a
+        opt_b.param_groups[0]["lr"] = lr_b
+        with torch.no_grad():
+            self._weight_all.clamp_(max=10)  # conf_optimize clip, optimizer_group.py:455-456
+        with torch.enable_grad():
+            self._run_phase(st, 0, min(start_b, niter), False)
+            if niter > start_b:
+                if self.has_invdepth:
+                    self.invalid_depth_group = self._set_st_depth()
+                    st["st"][:, 2] = 1.0
+                    if self.invalid_depth_group:
+                        st["st"][self.invalid_depth_group, 2] = 0.0
+                if self.has_traj:
+                    self.valid_traj_group_list, self.valid_group_idx = self._set_traj()
+                    st["valid_groups"] = torch.tensor(self.valid_traj_group_list, device=dev, dtype=torch.long)
+                    st["valid_idx"] = torch.tensor(self.valid_group_idx, device=dev, dtype=torch.long)
+                if self.verbose:
+                    print("invalid_depth_group", self.invalid_depth_group)
+                    print("valid_traj_group_list", self.valid_traj_group_list)
+                self._run_phase(st, start_b, niter, True)
+        torch.cuda.synchronize()
+        self._state = st
+        return self._current_loss(st, niter > start_b)

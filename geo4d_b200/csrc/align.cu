@@ -1,0 +1,454 @@
+// Geometry kernels of the per-window post-processing and the sliding-window alignment
+// (scripts/evaluation/infer_geo4d.py:447-500, utils/rays.py, dust3r/cloud_opt/*).  All fp32, HBM-bound:
+// every kernel is a single coalesced pass over the point maps with warp-shuffle + block reductions.
+#include "common.cuh"
+#include "geo4d_b200.h"
+
+namespace g4 {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Reduce NV per-thread partial sums over the block and atomically add them to dst[0..NV) (fp64 accumulators).
+template <int NV>
+__device__ __forceinline__ void block_reduce_atomic(float (&acc)[NV], double* dst) {
+  __shared__ float red[32][NV + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float s = warp_sum(acc[i]);
+    if (lane == 0) red[warp][i] = s;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NV; i += blockDim.x) {
+    double s = 0.0;
+    for (int w = 0; w < nw; ++w) s += (double)red[w][i];
+    atomicAdd(dst + i, s);
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------- K8
+// Per-window post-processing of the decoded maps (infer_geo4d.py:447-487): channels of `maps`
+// [11][T][H][W] = pts xyz, raw confidence, ray dir xyz, ray moment xyz, inverse depth (mean of 3 already).
+//   conf = softplus(c); invalid = sky(|v - 1.05| < eps on all 3) | far(any |v| > far_value)
+//   inv_conf = invalid ? 0 : 1/conf; pts = (x/alpha, y/beta, (z+1)/2); invdepth = (d+1)/2
+__global__ void postprocess_window_kernel(const float* __restrict__ maps, long long thw, float* __restrict__ pts,
+                                          float* __restrict__ inv_conf, float* __restrict__ invd,
+                                          unsigned char* __restrict__ valid, float sky_value, float sky_eps,
+                                          float far_value, float alpha, float beta, int has_conf) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < thw; i += (long long)gridDim.x * blockDim.x) {
+    const float x = maps[i], y = maps[thw + i], z = maps[2 * thw + i];
+    float conf = 1.0f;
+    if (has_conf) {
+      const float c = maps[3 * thw + i];
+      conf = (c > 20.0f) ? c : log1pf(__expf(c));  // nn.Softplus(beta=1, threshold=20)
+    }
+    const float lo = sky_value - sky_eps, hi = sky_value + sky_eps;
+    const bool sky = (x > lo) && (x < hi) && (y > lo) && (y < hi) && (z > lo) && (z < hi);
+    const bool far = (fabsf(x) > far_value) || (fabsf(y) > far_value) || (fabsf(z) > far_value);
+    const bool invalid = sky || far;
+    inv_conf[i] = invalid ? 0.0f : 1.0f / conf;
+    pts[3 * i + 0] = x / alpha;
+    pts[3 * i + 1] = y / beta;
+    pts[3 * i + 2] = (z + 1.0f) / 2.0f;
+    invd[i] = (maps[10 * thw + i] + 1.0f) / 2.0f;
+    if (valid) valid[i] = invalid ? 0 : valid[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- a14
+// Ray map -> per-frame camera moments (utils/rays.py:301-367,387-433,579-595; utils/normalize.py:25-51).
+// For frame t over the centre-cropped square: d = normalize(raydir), p = d x m,
+//   M += I - d d^T (6 unique), b += (I - d d^T) p (3), Hm += d_t (x) d_0 (9)   -> out[t][18] (fp64)
+__global__ void raymap_moments_kernel(const float* __restrict__ raydir, const float* __restrict__ raymom, int T,
+                                      int H, int W, int x0, int y0, int S, double* __restrict__ out) {
+  const int t = blockIdx.y;
+  const long long hw = (long long)H * W, thw = hw * T;
+  float acc[18];
+#pragma unroll
+  for (int i = 0; i < 18; ++i) acc[i] = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S * S; i += gridDim.x * blockDim.x) {
+    const int yy = y0 + i / S, xx = x0 + i % S;
+    const long long o = (long long)t * hw + (long long)yy * W + xx;  // channel-major [3][T][H][W]
+    const long long o0 = (long long)yy * W + xx;
+    float dx = raydir[o], dy = raydir[thw + o], dz = raydir[2 * thw + o];
+    const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+    dx *= inv; dy *= inv; dz *= inv;
+    float ax = raydir[o0], ay = raydir[thw + o0], az = raydir[2 * thw + o0];
+    const float ia = 1.0f / sqrtf(ax * ax + ay * ay + az * az);
+    ax *= ia; ay *= ia; az *= ia;
+    const float mx = raymom[o], my = raymom[thw + o], mz = raymom[2 * thw + o];
+    const float px = dy * mz - dz * my, py = dz * mx - dx * mz, pz = dx * my - dy * mx;  // p = d x m
+    // intersect_skew_lines_high_dim re-normalises r (already unit) -> I - d d^T
+    const float c00 = 1.f - dx * dx, c01 = -dx * dy, c02 = -dx * dz, c11 = 1.f - dy * dy, c12 = -dy * dz,
+                c22 = 1.f - dz * dz;
+    acc[0] += c00; acc[1] += c01; acc[2] += c02; acc[3] += c11; acc[4] += c12; acc[5] += c22;
+    acc[6] += c00 * px + c01 * py + c02 * pz;
+    acc[7] += c01 * px + c11 * py + c12 * pz;
+    acc[8] += c02 * px + c12 * py + c22 * pz;
+    // H = B^T A with B = frame-t dirs, A = frame-0 dirs: H[i][j] = sum b_i a_j
+    acc[9] += dx * ax;  acc[10] += dx * ay; acc[11] += dx * az;
+    acc[12] += dy * ax; acc[13] += dy * ay; acc[14] += dy * az;
+    acc[15] += dz * ax; acc[16] += dz * ay; acc[17] += dz * az;
+  }
+  block_reduce_atomic<18>(acc, out + (long long)t * 18);
+}
+
+// ---------------------------------------------------------------------------------------------- K9
+// Weighted Umeyama moments (what roma.rigid_points_registration reduces; init_im_poses.py:797-800).
+// pass 0: out[0..7)  = {sum w, sum w x(3), sum w y(3)}
+// pass 1: out[0..10) = {sum w |x-xm|^2, sum w (y-ym)(x-xm)^T (9, row-major [i=y][j=x])}  given means[6]
+__global__ void umeyama_moments_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                       const float* __restrict__ w1, const float* __restrict__ w2, long long n,
+                                       int pass, const double* __restrict__ means, double* __restrict__ out) {
+  float acc[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) acc[i] = 0.f;
+  float xm0 = 0, xm1 = 0, xm2 = 0, ym0 = 0, ym1 = 0, ym2 = 0;
+  if (pass == 1) {
+    xm0 = (float)means[0]; xm1 = (float)means[1]; xm2 = (float)means[2];
+    ym0 = (float)means[3]; ym1 = (float)means[4]; ym2 = (float)means[5];
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float w = w1[i];
+    if (w2) w *= w2[i];
+    const float a0 = x[3 * i], a1 = x[3 * i + 1], a2 = x[3 * i + 2];
+    const float b0 = y[3 * i], b1 = y[3 * i + 1], b2 = y[3 * i + 2];
+    if (pass == 0) {
+      acc[0] += w;
+      acc[1] += w * a0; acc[2] += w * a1; acc[3] += w * a2;
+      acc[4] += w * b0; acc[5] += w * b1; acc[6] += w * b2;
+    } else {
+      const float p0 = a0 - xm0, p1 = a1 - xm1, p2 = a2 - xm2;
+      const float q0 = b0 - ym0, q1 = b1 - ym1, q2 = b2 - ym2;
+      acc[0] += w * (p0 * p0 + p1 * p1 + p2 * p2);
+      acc[1] += w * q0 * p0; acc[2] += w * q0 * p1; acc[3] += w * q0 * p2;
+      acc[4] += w * q1 * p0; acc[5] += w * q1 * p1; acc[6] += w * q1 * p2;
+      acc[7] += w * q2 * p0; acc[8] += w * q2 * p1; acc[9] += w * q2 * p2;
+    }
+  }
+  block_reduce_atomic<10>(acc, out);
+}
+
+// ---------------------------------------------------------------------------------------------- K10
+// One fused iteration of the global alignment objective (optimizer_group.py:440-525) for the dense
+// part: per image n and pixel p
+//   X_w = R_n (d (u-cx)/f, d (v-cy)/f, d) + T_n,  d = exp(logd[n][p])
+//   L1 += w ||X_w - S_g pred_e[p]|| / A  over the edges e = (g, frame) that observe image n
+//   L2 += 2 m |1/(d+1e-6) - (s_g rho_e[p] + t_g)| / A                    (phase B, it >= 150)
+// It applies the Adam update to logd[n][p] in place (torch.optim.Adam formula, betas (0.9, 0.9)) and
+// reduces the gradients w.r.t. the small parameters in matrix form:
+//   gpose[n][12] = dL/d[R_n | T_n],  gS[g][12] = dL/d(s_g [R_g | T_g]),  gscal = {dL/d(1/f), L1, L2},
+//   gst[g][2] = {dL/ds_g, dL/dt_g}
+// The chain rule to quaternions / log-scales and the O(N) pose terms run on the host-side module.
+constexpr int AL_KMAX = 8;
+
+struct AlignIterArgs {
+  float* logd; float* adam_m; float* adam_v;  // [N][HW]
+  const float* pred;    // [E][HW][3]
+  const float* weight;  // [E][HW]
+  const float* invd;    // [E][HW] or null
+  const int* edge_ptr;  // [N+1]
+  const int* edge_idx;  // edges incident to each image
+  const float* poses;   // [N][12] c2w rows
+  const float* S;       // [G][12]
+  const float* scal;    // [iters][8] rows {1/f slot (unused), cx, cy, lr, bias_corr1, bias_corr2_sqrt, inv_area, phaseB}
+  const float* invf;    // [1] current 1/f
+  const int* it;        // device iteration counter selecting the scal row (null -> row 0)
+  const float* st;      // [G][3] {s, t, depth_valid}
+  double* gpose; double* gS; double* gscal; double* gst;
+  int N, HW, W, group_size;
+};
+
+__global__ void __launch_bounds__(256)
+align_iter_kernel(const AlignIterArgs a) {
+  const int n = blockIdx.y;
+  const int e0 = a.edge_ptr[n], ne = min(a.edge_ptr[n + 1] - e0, AL_KMAX);
+  const float* sc = a.scal + (a.it ? (long long)(*a.it) * 8 : 0);
+  const float invf = a.invf[0], cx = sc[1], cy = sc[2], lr = sc[3], bc1 = sc[4], bc2s = sc[5], invA = sc[6];
+  const bool phaseB = sc[7] != 0.f && a.invd != nullptr;
+  float R[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) R[i] = a.poses[n * 12 + i];
+  float acc[15];  // gR(9) gT(3) ginvf li dl  -> 15
+#pragma unroll
+  for (int i = 0; i < 15; ++i) acc[i] = 0.f;
+  float accS[AL_KMAX][14];  // dL/dS (12), dL/ds, dL/dt per incident edge slot
+#pragma unroll
+  for (int k = 0; k < AL_KMAX; ++k)
+#pragma unroll
+    for (int i = 0; i < 14; ++i) accS[k][i] = 0.f;
+
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < a.HW; p += gridDim.x * blockDim.x) {
+    const long long ip = (long long)n * a.HW + p;
+    const float ld = a.logd[ip];
+    const float d = __expf(ld);
+    const float du = (float)(p % a.W) - cx, dv = (float)(p / a.W) - cy;
+    const float xc = d * du * invf, yc = d * dv * invf, zc = d;
+    const float Xw0 = R[0] * xc + R[1] * yc + R[2] * zc + R[3];
+    const float Xw1 = R[4] * xc + R[5] * yc + R[6] * zc + R[7];
+    const float Xw2 = R[8] * xc + R[9] * yc + R[10] * zc + R[11];
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f, ginv = 0.f;
+    const float inv = 1.0f / (d + 1e-6f);
+#pragma unroll
+    for (int k = 0; k < AL_KMAX; ++k) {
+      if (k < ne) {
+        const int e = a.edge_idx[e0 + k];
+        const int g = e / a.group_size;
+        const long long ep = (long long)e * a.HW + p;
+        const float p0 = a.pred[3 * ep], p1 = a.pred[3 * ep + 1], p2 = a.pred[3 * ep + 2];
+        const float* Sg = a.S + g * 12;
+        const float Y0 = Sg[0] * p0 + Sg[1] * p1 + Sg[2] * p2 + Sg[3];
+        const float Y1 = Sg[4] * p0 + Sg[5] * p1 + Sg[6] * p2 + Sg[7];
+        const float Y2 = Sg[8] * p0 + Sg[9] * p1 + Sg[10] * p2 + Sg[11];
+        const float r0 = Xw0 - Y0, r1 = Xw1 - Y1, r2 = Xw2 - Y2;
+        const float nr = sqrtf(r0 * r0 + r1 * r1 + r2 * r2);
+        const float w = fminf(a.weight[ep], 10.0f);
+        acc[13] += w * nr;
+        const float c = nr > 0.f ? w * invA / nr : 0.f;  // torch norm backward is 0 at the origin
+        const float q0 = c * r0, q1 = c * r1, q2 = c * r2;
+        g0 += q0; g1 += q1; g2 += q2;
+        accS[k][0] -= q0 * p0; accS[k][1] -= q0 * p1; accS[k][2] -= q0 * p2; accS[k][3] -= q0;
+        accS[k][4] -= q1 * p0; accS[k][5] -= q1 * p1; accS[k][6] -= q1 * p2; accS[k][7] -= q1;
+        accS[k][8] -= q2 * p0; accS[k][9] -= q2 * p1; accS[k][10] -= q2 * p2; accS[k][11] -= q2;
+        if (phaseB) {
+          const float sg = a.st[g * 3], tg = a.st[g * 3 + 1], okg = a.st[g * 3 + 2];
+          const float rho = a.invd[ep];
+          const float m = (rho > 0.05f && okg != 0.f) ? 1.f : 0.f;
+          const float res = inv - (sg * rho + tg);
+          acc[14] += m * fabsf(res);
+          const float sgn = (res > 0.f) ? 1.f : ((res < 0.f) ? -1.f : 0.f);
+          const float gl = sgn * m * 2.0f * invA;
+          ginv += gl;
+          accS[k][12] -= gl * rho;
+          accS[k][13] -= gl;
+        }
+      }
+    }
+    // gradient w.r.t. depth, then log-depth
+    const float jx = R[0] * du * invf + R[1] * dv * invf + R[2];
+    const float jy = R[4] * du * invf + R[5] * dv * invf + R[6];
+    const float jz = R[8] * du * invf + R[9] * dv * invf + R[10];
+    const float gd = g0 * jx + g1 * jy + g2 * jz - ginv * inv * inv;
+    const float grad = gd * d;
+    // torch.optim.Adam (no weight decay, no amsgrad): betas (0.9, 0.9), eps 1e-8
+    const float m1 = 0.9f * a.adam_m[ip] + 0.1f * grad;
+    const float v1 = 0.9f * a.adam_v[ip] + 0.1f * grad * grad;
+    a.adam_m[ip] = m1;
+    a.adam_v[ip] = v1;
+    a.logd[ip] = ld - (lr / bc1) * m1 / (sqrtf(v1) / bc2s + 1e-8f);
+    // pose / focal gradients
+    acc[0] += g0 * xc; acc[1] += g0 * yc; acc[2] += g0 * zc;
+    acc[3] += g1 * xc; acc[4] += g1 * yc; acc[5] += g1 * zc;
+    acc[6] += g2 * xc; acc[7] += g2 * yc; acc[8] += g2 * zc;
+    acc[9] += g0; acc[10] += g1; acc[11] += g2;
+    acc[12] += d * (g0 * (R[0] * du + R[1] * dv) + g1 * (R[4] * du + R[5] * dv) + g2 * (R[8] * du + R[9] * dv));
+  }
+  // ---- reductions
+  {
+    float pose[12];
+    pose[0] = acc[0]; pose[1] = acc[1]; pose[2] = acc[2]; pose[3] = acc[9];
+    pose[4] = acc[3]; pose[5] = acc[4]; pose[6] = acc[5]; pose[7] = acc[10];
+    pose[8] = acc[6]; pose[9] = acc[7]; pose[10] = acc[8]; pose[11] = acc[11];
+    block_reduce_atomic<12>(pose, a.gpose + (long long)n * 12);
+    float s3[3] = {acc[12], acc[13], acc[14]};
+    block_reduce_atomic<3>(s3, a.gscal);
+  }
+#pragma unroll
+  for (int k = 0; k < AL_KMAX; ++k) {
+    if (k < ne) {  // uniform across the block
+      const int g = a.edge_idx[e0 + k] / a.group_size;
+      float s12[12];
+#pragma unroll
+      for (int i = 0; i < 12; ++i) s12[i] = accS[k][i];
+      block_reduce_atomic<12>(s12, a.gS + (long long)g * 12);
+      float s2[2] = {accS[k][12], accS[k][13]};
+      block_reduce_atomic<2>(s2, a.gst + (long long)g * 2);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- K11
+// LAD scale/shift fit  min sum |s x + t - y|  with the reference's optimiser (Adam, default betas
+// (0.9, 0.999), eps 1e-8; depth_eval.py:112-145), batched over G windows.  Two kernels per iteration:
+// lad_grad reduces {sum sign(r) x, sum sign(r), sum |r|}; lad_update applies Adam to (s, t), checks the
+// |delta loss| < tol early exit and clears the accumulators.  state[g] = {s, t, m_s, v_s, m_t, v_t,
+// prev_loss, step, done}.
+__global__ void lad_grad_kernel(const float* __restrict__ x, const float* __restrict__ y, long long n_per_group,
+                                const float* __restrict__ state, double* __restrict__ acc) {
+  const int g = blockIdx.y;
+  if (state[g * 9 + 8] != 0.f) return;
+  const float s = state[g * 9], t = state[g * 9 + 1];
+  const float* xg = x + (long long)g * n_per_group;
+  const float* yg = y + (long long)g * n_per_group;
+  float a[3] = {0.f, 0.f, 0.f};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_per_group;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float xv = xg[i];
+    const float r = s * xv + t - yg[i];
+    const float sgn = (r > 0.f) ? 1.f : ((r < 0.f) ? -1.f : 0.f);
+    a[0] += sgn * xv;
+    a[1] += sgn;
+    a[2] += fabsf(r);
+  }
+  block_reduce_atomic<3>(a, acc + g * 3);
+}
+
+__global__ void lad_update_kernel(float* __restrict__ state, double* __restrict__ acc, int G, float lr, float tol) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  float* st = state + g * 9;
+  if (st[8] == 0.f) {
+    const float gs = (float)acc[g * 3], gt = (float)acc[g * 3 + 1], loss = (float)acc[g * 3 + 2];
+    const float step = st[7] + 1.f;
+    const float bc1 = 1.f - powf(0.9f, step), bc2 = 1.f - powf(0.999f, step);
+    st[2] = 0.9f * st[2] + 0.1f * gs;
+    st[3] = 0.999f * st[3] + 0.001f * gs * gs;
+    st[4] = 0.9f * st[4] + 0.1f * gt;
+    st[5] = 0.999f * st[5] + 0.001f * gt * gt;
+    st[0] -= (lr / bc1) * st[2] / (sqrtf(st[3]) / sqrtf(bc2) + 1e-8f);
+    st[1] -= (lr / bc1) * st[4] / (sqrtf(st[5]) / sqrtf(bc2) + 1e-8f);
+    if (st[7] > 0.f && fabsf(st[6] - loss) < tol) st[8] = 1.f;  // converged: stop after this update
+    st[6] = loss;
+    st[7] = step;
+  }
+  acc[g * 3] = 0.0; acc[g * 3 + 1] = 0.0; acc[g * 3 + 2] = 0.0;
+}
+
+// delta < 1.25 accuracy of s*x + t against y under mask (depth_eval.py:296-317): out[g] = {count_ok, count}
+__global__ void delta125_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                const float* __restrict__ w, long long n_per_group, const float* __restrict__ st,
+                                int st_stride, double* __restrict__ out) {
+  const int g = blockIdx.y;
+  const float s = st[g * st_stride], t = st[g * st_stride + 1];
+  float a[2] = {0.f, 0.f};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_per_group;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long j = (long long)g * n_per_group + i;
+    const float xv = x[j], gt = y[j];
+    if (w[j] > 0.5f && xv > 0.05f && gt > 0.f) {
+      const float pr = fmaxf(s * xv + t, 1e-5f);
+      const float ratio = fmaxf(pr / gt, gt / pr);
+      a[0] += (ratio < 1.25f) ? 1.f : 0.f;
+      a[1] += 1.f;
+    }
+  }
+  block_reduce_atomic<2>(a, out + g * 2);
+}
+
+int device_sm_count();
+
+static inline int blocks_for(long long n, int cap) {
+  long long b = (n + 255) / 256;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace g4
+
+using namespace g4;
+#define G4_STREAM cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_)
+
+extern "C" int geo4d_postprocess_window(const float* maps, int64_t thw, float* pts, float* inv_conf, float* invdepth,
+                                        unsigned char* valid, float sky_value, float sky_eps, float far_value,
+                                        float alpha, float beta, int has_conf, g4_stream_t stream_) {
+  G4_STREAM;
+  if (!maps || !pts || !inv_conf || !invdepth) { set_last_error("postprocess_window: null"); return G4_ERR_BAD_ARG; }
+  const int sms = device_sm_count(); if (sms <= 0) return G4_ERR_CUDA;
+  postprocess_window_kernel<<<blocks_for(thw, sms * 8), 256, 0, stream>>>(maps, thw, pts, inv_conf, invdepth, valid,
+                                                                         sky_value, sky_eps, far_value, alpha, beta,
+                                                                         has_conf);
+  return check_launch("postprocess_window");
+}
+
+extern "C" int geo4d_raymap_moments(const float* raydir, const float* raymoment, int T, int H, int W, double* out,
+                                    g4_stream_t stream_) {
+  G4_STREAM;
+  if (!raydir || !raymoment || !out || T < 1 || T > 65535) { set_last_error("raymap_moments: bad args"); return G4_ERR_BAD_ARG; }
+  const int S = H < W ? H : W;
+  const int x0 = (W - S) / 2, y0 = (H - S) / 2;
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(double) * 18 * T, stream);
+  if (e != cudaSuccess) { set_last_error("raymap_moments: memset: %s", cudaGetErrorString(e)); return G4_ERR_CUDA; }
+  dim3 grid(blocks_for((long long)S * S, 32), T);
+  raymap_moments_kernel<<<grid, 256, 0, stream>>>(raydir, raymoment, T, H, W, x0, y0, S, out);
+  return check_launch("raymap_moments");
+}
+
+extern "C" int geo4d_umeyama_moments(const float* x, const float* y, const float* w1, const float* w2, int64_t n,
+                                     int pass, const double* means, double* out, g4_stream_t stream_) {
+  G4_STREAM;
+  if (!x || !y || !w1 || !out || (pass == 1 && !means) || pass < 0 || pass > 1) {
+    set_last_error("umeyama_moments: bad args"); return G4_ERR_BAD_ARG;
+  }
+  const int sms = device_sm_count(); if (sms <= 0) return G4_ERR_CUDA;
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(double) * 10, stream);
+  if (e != cudaSuccess) { set_last_error("umeyama_moments: memset: %s", cudaGetErrorString(e)); return G4_ERR_CUDA; }
+  umeyama_moments_kernel<<<blocks_for(n, sms * 4), 256, 0, stream>>>(x, y, w1, w2, n, pass, means, out);
+  return check_launch("umeyama_moments");
+}
+
+extern "C" int geo4d_align_iter(float* logd, float* adam_m, float* adam_v, const float* pred, const float* weight,
+                                const float* invd, const int* edge_ptr, const int* edge_idx, const float* poses,
+                                const float* S, const float* scal, const float* invf, const int* it, const float* st,
+                                double* gpose, double* gS, double* gscal, double* gst, int N, int G, int HW, int W,
+                                int group_size, int max_edges_per_image, g4_stream_t stream_) {
+  G4_STREAM;
+  if (!logd || !adam_m || !adam_v || !pred || !weight || !edge_ptr || !edge_idx || !poses || !S || !scal || !invf || !st ||
+      !gpose || !gS || !gscal || !gst) { set_last_error("align_iter: null pointer"); return G4_ERR_BAD_ARG; }
+  if (max_edges_per_image > AL_KMAX) {
+    set_last_error("align_iter: an image is observed by %d windows; at most %d supported", max_edges_per_image, AL_KMAX);
+    return G4_ERR_UNSUPPORTED;
+  }
+  if (N < 1 || N > 65535) { set_last_error("align_iter: N=%d", N); return G4_ERR_BAD_ARG; }
+  cudaError_t e = cudaMemsetAsync(gpose, 0, sizeof(double) * 12 * N, stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(gS, 0, sizeof(double) * 12 * G, stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(gscal, 0, sizeof(double) * 3, stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(gst, 0, sizeof(double) * 2 * G, stream);
+  if (e != cudaSuccess) { set_last_error("align_iter: memset: %s", cudaGetErrorString(e)); return G4_ERR_CUDA; }
+  AlignIterArgs a;
+  a.logd = logd; a.adam_m = adam_m; a.adam_v = adam_v; a.pred = pred; a.weight = weight; a.invd = invd;
+  a.edge_ptr = edge_ptr; a.edge_idx = edge_idx; a.poses = poses; a.S = S; a.scal = scal; a.invf = invf; a.it = it; a.st = st;
+  a.gpose = gpose; a.gS = gS; a.gscal = gscal; a.gst = gst;
+  a.N = N; a.HW = HW; a.W = W; a.group_size = group_size;
+  const int sms = device_sm_count(); if (sms <= 0) return G4_ERR_CUDA;
+  int bx = (4 * sms + N - 1) / N;
+  const int maxbx = (HW + 255) / 256;
+  if (bx > maxbx) bx = maxbx;
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, N);
+  align_iter_kernel<<<grid, 256, 0, stream>>>(a);
+  return check_launch("align_iter");
+}
+
+extern "C" int geo4d_lad_step(const float* x, const float* y, int64_t n_per_group, int G, float* state, double* acc,
+                              float lr, float tol, g4_stream_t stream_) {
+  G4_STREAM;
+  if (!x || !y || !state || !acc || G < 1 || G > 65535) { set_last_error("lad_step: bad args"); return G4_ERR_BAD_ARG; }
+  const int sms = device_sm_count(); if (sms <= 0) return G4_ERR_CUDA;
+  int bx = (2 * sms + G - 1) / G;
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, G);
+  lad_grad_kernel<<<grid, 256, 0, stream>>>(x, y, n_per_group, state, acc);
+  int rc = check_launch("lad_grad"); if (rc) return rc;
+  lad_update_kernel<<<(G + 63) / 64, 64, 0, stream>>>(state, acc, G, lr, tol);
+  return check_launch("lad_update");
+}
+
+extern "C" int geo4d_delta125(const float* x, const float* y, const float* w, int64_t n_per_group, int G,
+                              const float* st, int st_stride, double* out, g4_stream_t stream_) {
+  G4_STREAM;
+  if (!x || !y || !w || !st || !out || G < 1 || G > 65535) { set_last_error("delta125: bad args"); return G4_ERR_BAD_ARG; }
+  const int sms = device_sm_count(); if (sms <= 0) return G4_ERR_CUDA;
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(double) * 2 * G, stream);
+  if (e != cudaSuccess) { set_last_error("delta125: memset: %s", cudaGetErrorString(e)); return G4_ERR_CUDA; }
+  int bx = (2 * sms + G - 1) / G;
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, G);
+  delta125_kernel<<<grid, 256, 0, stream>>>(x, y, w, n_per_group, st, st_stride, out);
+  return check_launch("delta125");
+}

@@ -10,6 +10,7 @@
 namespace g4 {
 
 static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;
 
 void set_last_error(const char* fmt, ...) {
   va_list ap;
@@ -25,6 +26,7 @@ int check_launch(const char* what) {
     (void)cudaGetLastError();
     return G4_ERR_CUDA;
   }
+  ++g_launches;
   return G4_OK;
 }
 
@@ -99,6 +101,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 }  // namespace g4
 
 extern "C" int geo4d_abi_version(void) { return GEO4D_ABI_VERSION; }
+extern "C" uint64_t geo4d_launch_count(void) { return g4::g_launches; }
 extern "C" const char* geo4d_last_error(void) { return g4::g_err; }
 extern "C" int geo4d_device_supported(void) {
   int dev = 0;

@@ -288,3 +288,68 @@ def transpose_bf16(x: torch.Tensor, batch: int, R: int, Cc: int, out: Optional[t
     check(lib().geo4d_transpose_bf16(_vp(x), C.c_int64(x.stride(0)), _vp(out), batch, R, Cc, _s()),
           "geo4d_transpose_bf16")
     return out
+
+
+# --------------------------------------------------------------------------- geometry kernels
+def postprocess_window(maps: torch.Tensor, T: int, H: int, W: int, valid: Optional[torch.Tensor] = None,
+                       sky_eps: float = 0.1, far_value: float = 1.99, has_conf: bool = True):
+    """maps [11, T, H, W] fp32 contiguous -> (pts [T,H,W,3], inv_conf [T,H,W,1], invdepth [T,H,W,1])."""
+    assert maps.is_contiguous() and maps.dtype == torch.float32 and maps.shape[0] == 11
+    thw = T * H * W
+    pts = torch.empty((T, H, W, 3), device=maps.device, dtype=torch.float32)
+    conf = torch.empty((T, H, W, 1), device=maps.device, dtype=torch.float32)
+    invd = torch.empty((T, H, W, 1), device=maps.device, dtype=torch.float32)
+    check(lib().geo4d_postprocess_window(_vp(maps), C.c_int64(thw), _vp(pts), _vp(conf), _vp(invd), _vp(valid),
+                                         C.c_float(1.05), C.c_float(sky_eps), C.c_float(far_value), C.c_float(2.0),
+                                         C.c_float(2.0), 1 if has_conf else 0, _s()), "geo4d_postprocess_window")
+    return pts, conf, invd
+
+
+def raymap_moments(raydir: torch.Tensor, raymoment: torch.Tensor, T: int, H: int, W: int) -> torch.Tensor:
+    """raydir / raymoment [3, T, H, W] fp32 contiguous -> [T, 18] fp64 moments."""
+    assert raydir.is_contiguous() and raymoment.is_contiguous()
+    out = torch.empty((T, 18), device=raydir.device, dtype=torch.float64)
+    check(lib().geo4d_raymap_moments(_vp(raydir), _vp(raymoment), T, H, W, _vp(out), _s()), "geo4d_raymap_moments")
+    return out
+
+
+def umeyama_moments(x: torch.Tensor, y: torch.Tensor, w1: torch.Tensor, w2: Optional[torch.Tensor], npts: int,
+                    pass_: int, means: Optional[torch.Tensor]) -> torch.Tensor:
+    out = torch.empty(10, device=x.device, dtype=torch.float64)
+    check(lib().geo4d_umeyama_moments(_vp(x), _vp(y), _vp(w1), _vp(w2), C.c_int64(npts), pass_, _vp(means), _vp(out),
+                                      _s()), "geo4d_umeyama_moments")
+    return out
+
+
+def lad_step(x, y, n_per_group: int, G: int, state, acc, lr: float, tol: float = 1e-6):
+    check(lib().geo4d_lad_step(_vp(x), _vp(y), C.c_int64(n_per_group), G, _vp(state), _vp(acc), C.c_float(lr),
+                               C.c_float(tol), _s()), "geo4d_lad_step")
+
+
+def delta125(x, y, w, n_per_group: int, G: int, st, st_stride: int) -> torch.Tensor:
+    out = torch.empty((G, 2), device=x.device, dtype=torch.float64)
+    check(lib().geo4d_delta125(_vp(x), _vp(y), _vp(w), C.c_int64(n_per_group), G, _vp(st), st_stride, _vp(out), _s()),
+          "geo4d_delta125")
+    return out
+
+
+# --------------------------------------------------------------------------- launch accounting
+_replayed_kernels = 0
+
+
+def launch_count() -> int:
+    """Kernels launched by libgeo4d_b200 so far: direct launches + kernels re-issued by CUDA-graph replays."""
+    f = lib().geo4d_launch_count
+    f.restype = C.c_uint64
+    return int(f()) + _replayed_kernels
+
+
+def raw_launch_count() -> int:
+    f = lib().geo4d_launch_count
+    f.restype = C.c_uint64
+    return int(f())
+
+
+def note_replay(kernels_in_graph: int, times: int = 1) -> None:
+    global _replayed_kernels
+    _replayed_kernels += kernels_in_graph * times

@@ -68,6 +68,9 @@ class DDIMSampler(object):
             cbs = (c0[0] if isinstance(c0, (list, tuple)) else c0).shape[0]
             if cbs != batch_size:
                 print(f"Warning: Got {cbs} conditionings but batch-size is {batch_size}")
+        # the evaluation script forwards inert extras (cfg_img=None, unconditional_conditioning_img_nonetext=None,
+        # infer_geo4d.py:188-226) that the reference U-Net swallows in **kwargs
+        kwargs = {k: v for k, v in kwargs.items() if v is not None}
         self.make_schedule(ddim_num_steps=S, ddim_discretize=timestep_spacing, ddim_eta=eta, verbose=schedule_verbose)
         if len(shape) == 3:
             size = (batch_size, *shape)
@@ -152,15 +155,19 @@ class DDIMSampler(object):
                 g = torch.cuda.CUDAGraph()
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
+                n0 = ops.raw_launch_count()
                 with torch.cuda.stream(side):
                     with torch.cuda.graph(g, stream=side):
                         one_step()
                 torch.cuda.current_stream().wait_stream(side)
                 st["graph"] = g
+                st["graph_kernels"] = ops.raw_launch_count() - n0
+                ops.note_replay(st["graph_kernels"], -1)  # the capture pass recorded, it did not execute
                 # capture does not execute: the counter still points at step 1
         for i in range(first, S):
             index = S - i - 1
             st["graph"].replay()
+            ops.note_replay(st["graph_kernels"])
             if index % log_every_t == 0 or index == S - 1:
                 inter["x_inter"].append(st["x"].clone())
                 inter["pred_x0"].append(st["pred_x0"].clone())

@@ -38,6 +38,8 @@ int geo4d_abi_version(void);
 const char* geo4d_last_error(void);
 /* 1 if the current device is compute capability 10.x (tcgen05/TMEM present). */
 int geo4d_device_supported(void);
+/* Number of kernels this library has launched (or recorded into a CUDA graph) in this process. */
+uint64_t geo4d_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Tap-GEMM on tcgen05 tensor cores (TMA -> shared memory -> tcgen05.mma -> TMEM -> epilogue).
@@ -143,6 +145,42 @@ int geo4d_gather_row(const float* table, int64_t ld, const int* idx, float* out,
 int geo4d_softmax_rows(const float* s, int64_t lds, void* p_bf16, int64_t ldp, int64_t rows, int cols,
                        g4_stream_t stream);
 int geo4d_transpose_bf16(const void* in, int64_t ldin, void* out, int batch, int R, int C, g4_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Geometry: per-window post-processing and sliding-window alignment (all fp32, HBM-bound reductions).
+ * ---------------------------------------------------------------------------------------------- */
+/* infer_geo4d.py:447-487 fused: softplus(conf), sky / far masks, 1/conf, de-normalisation, (d+1)/2.
+ * maps = [11][T][H][W] decoded channels (pts xyz, conf, ray dir xyz, ray moment xyz, inverse depth);
+ * outputs pts [T*H*W][3], inv_conf / invdepth [T*H*W]; `valid` (optional) is AND-ed with ~invalid. */
+int geo4d_postprocess_window(const float* maps, int64_t thw, float* pts, float* inv_conf, float* invdepth,
+                             unsigned char* valid, float sky_value, float sky_eps, float far_value, float alpha,
+                             float beta, int has_conf, g4_stream_t stream);
+/* Pluecker ray map -> per-frame moments for the camera solve (utils/rays.py:301-367,387-433,579-595;
+ * utils/normalize.py:25-51): out[t][18] = {sum(I - d d^T) (6 unique), sum (I - d d^T)(d x m) (3),
+ * sum d_t (x) d_0 (9)} over the centre-cropped square; raydir/raymoment are [3][T][H][W]. */
+int geo4d_raymap_moments(const float* raydir, const float* raymoment, int T, int H, int W, double* out,
+                         g4_stream_t stream);
+/* Weighted Umeyama moments = the reductions of roma.rigid_points_registration(x, y, weights=w1*w2,
+ * compute_scaling=True) (init_im_poses.py:797-800).  pass 0: out = {sum w, sum w x(3), sum w y(3)};
+ * pass 1 (means = {xm(3), ym(3)}): out = {sum w|x-xm|^2, sum w (y-ym)(x-xm)^T (9)}.  out: 10 doubles. */
+int geo4d_umeyama_moments(const float* x, const float* y, const float* w1, const float* w2, int64_t n, int pass,
+                          const double* means, double* out, g4_stream_t stream);
+/* One fused iteration of the dense part of LightPointCloudGroupOptimizer.forward + backward + Adam on the
+ * log-depth maps (optimizer_group.py:440-525; base_opt_group.py:593-626).  See csrc/align.cu for the
+ * layout of scal / st and the reduced gradient outputs (all fp64, zeroed by the call). */
+int geo4d_align_iter(float* logd, float* adam_m, float* adam_v, const float* pred, const float* weight,
+                     const float* invd, const int* edge_ptr, const int* edge_idx, const float* poses,
+                     const float* S, const float* scal, const float* invf, const int* it, const float* st,
+                     double* gpose, double* gS, double* gscal, double* gst, int N, int G, int HW, int W,
+                     int group_size, int max_edges_per_image, g4_stream_t stream);
+/* One Adam iteration of the LAD scale/shift fit min sum|s x + t - y| for G windows at once
+ * (absolute_value_scaling2 depth_eval.py:112-145).  state[g] = {s, t, m_s, v_s, m_t, v_t, prev_loss,
+ * step, done}; acc = 3*G doubles, zero before the first call. */
+int geo4d_lad_step(const float* x, const float* y, int64_t n_per_group, int G, float* state, double* acc, float lr,
+                   float tol, g4_stream_t stream);
+/* delta<1.25 accuracy of s*x+t vs y under (w>0.5 & x>0.05 & y>0) (depth_eval.py:296-317): out[g] = {ok, n}. */
+int geo4d_delta125(const float* x, const float* y, const float* w, int64_t n_per_group, int G, const float* st,
+                   int st_stride, double* out, g4_stream_t stream);
 
 #ifdef __cplusplus
 }

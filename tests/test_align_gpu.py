@@ -1,0 +1,109 @@
+"""GPU: geometry kernels and the CUDA aligner (through the C ABI) vs the CPU oracle on seeded inputs.
+Tolerances: closed-form pieces 1e-4 relative; iterated alignment outputs: depth AbsRel
+between implementations <= 1e-2, camera centres <= 1e-2 scene units, rotations <= 0.1 deg, focal <= 1e-2 rel."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_postprocess_and_raymap_vs_oracle(cuda_device):
+    from oracle import align as oa
+    from geo4d_b200.pipeline import Geo4DPipeline, raymap_to_camera_matrix
+    from geo4d_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    T, H, W = 4, 24, 40
+    maps = torch.randn(1, 11, T, H, W, generator=g) * 0.8
+    maps[0, 0:3, :, :3, :5] = 1.05 + 0.05 * torch.randn(3, T, 3, 5, generator=g)  # sky pixels
+    maps[0, 0, :, 5, 5] = 2.5                                                      # far pixels
+    maps[0, 6] = maps[0, 6].abs() + 0.5                                            # rays look forward
+    ref = oa.postprocess_window(maps)
+    md = maps.to(cuda_device)
+    valid = torch.ones(T, H, W, dtype=torch.uint8, device=cuda_device)
+    pts, conf, invd = ops.postprocess_window(md[0].contiguous(), T, H, W, valid=valid)
+    traj = raymap_to_camera_matrix(md[:, 4:7], md[:, 7:10])
+    torch.cuda.synchronize()
+    assert torch.allclose(pts.cpu(), ref["pts3d"], atol=1e-6)
+    assert torch.allclose(conf.cpu(), ref["conf"], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(invd.cpu(), ref["inverse_depthmap"], atol=1e-6)
+    assert torch.equal(valid.cpu().bool().unsqueeze(-1), ref["valid"])
+    assert torch.allclose(traj.cpu(), ref["traj"], atol=2e-4)
+
+
+def test_umeyama_kernel_vs_oracle(cuda_device):
+    from oracle import align as oa
+    from geo4d_b200.cloud_opt import umeyama_from_moments
+    from geo4d_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    n = 50000
+    x = torch.randn(n, 3, generator=g) * 2 + 5
+    q = torch.randn(4, generator=g)
+    R = oa.unitquat_to_rotmat(q / q.norm())
+    y = 0.7 * x @ R.T + torch.tensor([1.0, -2.0, 3.0]) + 0.01 * torch.randn(n, 3, generator=g)
+    w1, w2 = torch.rand(n, generator=g), torch.rand(n, generator=g)
+    Rr, tr, sr = oa.rigid_points_registration(x, y, weights=w1 * w2, compute_scaling=True)
+    xd, yd, w1d, w2d = (t.to(cuda_device).contiguous() for t in (x, y, w1, w2))
+    m0 = ops.umeyama_moments(xd, yd, w1d, w2d, n, 0, None)
+    m1 = ops.umeyama_moments(xd, yd, w1d, w2d, n, 1, (m0[1:7] / m0[0]).contiguous())
+    s, Rg, Tg = umeyama_from_moments(m0.cpu().numpy(), m1.cpu().numpy())
+    assert abs(s - float(sr)) < 1e-5
+    assert np.allclose(Rg, Rr.numpy(), atol=1e-5) and np.allclose(Tg, tr.numpy(), atol=1e-4)
+
+
+def test_lad_fit_vs_oracle(cuda_device):
+    from oracle import align as oa
+    from geo4d_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    G, n = 2, 4000
+    x = torch.rand(G, n, generator=g) + 0.1
+    y = 2.5 * x - 0.3 + 0.05 * torch.randn(G, n, generator=g)
+    y[:, :100] += 3.0
+    iters = 300
+    xd, yd = x.to(cuda_device).contiguous(), y.to(cuda_device).contiguous()
+    state = torch.zeros(G, 9, device=cuda_device)
+    s0 = torch.median(y, dim=1).values / torch.median(x, dim=1).values
+    state[:, 0] = s0.to(cuda_device)
+    acc = torch.zeros(G * 3, device=cuda_device, dtype=torch.float64)
+    for _ in range(iters):
+        ops.lad_step(xd, yd, n, G, state, acc, 1e-2)
+    torch.cuda.synchronize()
+    for gi in range(G):
+        s_ref, t_ref = oa.lad_adam(x[gi], y[gi], float(s0[gi]), 1e-2, iters)
+        assert abs(float(state[gi, 0]) - s_ref) < 2e-3 and abs(float(state[gi, 1]) - t_ref) < 2e-3
+    w = torch.ones(G, n, device=cuda_device)
+    d = ops.delta125(xd, yd, w, n, G, state, 9).cpu().numpy()
+    assert (d[:, 1] == n).all() and (d[:, 0] / d[:, 1] > 0.8).all()
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_aligner_vs_oracle(cuda_device, graph):
+    from oracle import align as oa
+    from geo4d_b200.cloud_opt import LightPointCloudGroupOptimizer
+    groups, preds, gt = oa.synthetic_scene(T=24, H=32, W=48, noise=0.003)
+    niter, start_b, lad = 40, 15, 300
+    ref = oa.GroupAligner(groups, preds, depth_traj_start_iter=start_b, lad_max_iters=lad)
+    ref.compute_global_alignment(niter=niter, lr=0.03, schedule="linear")
+    r = ref.results()
+    views = [[{"idx": (i,)} for i in g] for g in groups]
+    preds_d = [{k: v.to(cuda_device) for k, v in p.items()} for p in preds]
+    scene = LightPointCloudGroupOptimizer(views, preds_d, conf="id", conf_optimize=True, verbose=False,
+                                          shared_focal=True, num_total_iter=niter, temporal_smoothing_weight=0.015,
+                                          translation_weight=1.0, depth_traj_start_iter=start_b, lad_max_iters=lad,
+                                          use_cuda_graph=graph)
+    with torch.enable_grad():
+        scene.compute_global_alignment(init="group", niter=niter, schedule="linear", lr=0.03)
+    assert scene.invalid_depth_group == ref.invalid_depth_group
+    assert scene.valid_traj_group_list == ref.valid_traj_groups
+    depth = torch.stack(scene.get_depthmaps()).cpu()
+    absrel = float(((depth - r["depth"]).abs() / r["depth"]).mean())
+    assert absrel < 1e-2, absrel
+    P = scene.get_im_poses().detach().cpu()
+    assert float((P[:, :3, 3] - r["poses"][:, :3, 3]).norm(dim=-1).max()) < 1e-2
+    Rrel = torch.matmul(P[:, :3, :3].transpose(1, 2), r["poses"][:, :3, :3])
+    ang = torch.rad2deg(torch.acos(((Rrel.diagonal(dim1=1, dim2=2).sum(-1) - 1) / 2).clamp(-1, 1)))
+    assert float(ang.max()) < 0.1
+    assert abs(float(scene.get_focals()[0]) - r["focal"]) / r["focal"] < 1e-2
+    assert abs(float(scene.s_depth[0]) - float(r["s_depth"][0])) < 2e-2
