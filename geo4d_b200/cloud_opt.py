@@ -335,7 +335,18 @@ class LightPointCloudGroupOptimizer(nn.Module):
         dev = self.device
         pred = self._stacked_pred_all.view(G, gs, HW, 3)
         conf = self._weight_all.view(G, gs, HW)
-        focal_group = isv.focal_per_group(pred[:, 0].reshape(G, H, W, 3).cpu(), conf[:, 0].reshape(G, H, W).cpu())
+        try:
+            focal_group = isv.focal_per_group(pred[:, 0].reshape(G, H, W, 3).cpu(), conf[:, 0].reshape(G, H, W).cpu())
+            if not all(math.isfinite(f) for f in focal_group):
+                raise ValueError("non-finite focal")
+        except Exception:
+            # same fallback as align_group_prefix (init_im_poses.py:272-278): focal search by RANSAC-PnP on the
+            # first frame, shared by all windows
+            if self.verbose:
+                print("Error in computing focal length")
+            res = isv.fast_pnp(pred[0, 0].reshape(H, W, 3).cpu().numpy(), None,
+                               (conf[0, 0] > 0.5).reshape(H, W).cpu().numpy(), niter_PnP)
+            focal_group = [res[0] if res else float(max(H, W))] * G
         pts3d = torch.zeros(N, HW, 3, device=dev)
         conf_list = torch.zeros(N, HW, device=dev)
         im_poses: List[Optional[np.ndarray]] = [None] * N

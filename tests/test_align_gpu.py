@@ -59,7 +59,7 @@ def test_lad_fit_vs_oracle(cuda_device):
     g = torch.Generator().manual_seed(2)
     G, n = 2, 4000
     x = torch.rand(G, n, generator=g) + 0.1
-    y = 2.5 * x - 0.3 + 0.05 * torch.randn(G, n, generator=g)
+    y = 2.5 * x + 0.3 + 0.05 * torch.randn(G, n, generator=g)
     y[:, :100] += 3.0
     iters = 300
     xd, yd = x.to(cuda_device).contiguous(), y.to(cuda_device).contiguous()

@@ -109,3 +109,20 @@ def test_aligner_oracle_reduces_loss_and_recovers_geometry():
     d, dg = r["depth"].reshape(-1), gt["depth"].reshape(-1)
     sc = float((d * dg).sum() / (d * d).sum())
     assert float(((sc * d - dg).abs() / dg).mean()) < 0.08
+
+
+def test_aligner_oracle_matches_reference_golden(golden_dir):
+    """tests/golden/align_ref.pt holds the outputs of the reference's own LightPointCloudGroupOptimizer run
+    on CPU by oracle/gen_golden.py (roma/evo calls routed to the restatements above)."""
+    import os
+    ref = torch.load(os.path.join(golden_dir, "align_ref.pt"))
+    sc = ref["scene"]
+    groups, preds, _ = oa.synthetic_scene(T=sc["T"], H=sc["H"], W=sc["W"], noise=sc["noise"])
+    al = oa.GroupAligner(groups, preds, depth_traj_start_iter=sc["start_b"], lad_max_iters=5000)
+    al.compute_global_alignment(niter=sc["niter"], lr=0.03, schedule="linear")
+    r = al.results()
+    assert al.valid_traj_groups == ref["valid_traj"] and al.invalid_depth_group == ref["invalid_depth"]
+    assert float(((r["depth"] - ref["depth"]).abs() / ref["depth"]).mean()) < 1e-3
+    assert float((r["poses"] - ref["poses"]).abs().max()) < 1e-3
+    assert abs(r["focal"] - ref["focal"]) / ref["focal"] < 1e-3
+    assert float((r["s_depth"] - ref["s_depth"]).abs().max()) < 1e-2
