@@ -158,7 +158,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from geo4d_b200 import ops, synthetic
+    from geo4d_b200 import ops, sharding, synthetic
     from geo4d_b200.pipeline import Geo4DPipeline, sliding_windows
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -174,25 +174,13 @@ def main():
     video_host = synthetic.synthetic_video(T, H, W, device="cpu", seed=123).pin_memory()
     video_dev = video_host.to(dev, non_blocking=True)
     my = windows[rank]
-    hw5 = 16 * H * W * 5 + 256
 
     def step(video):
         """this rank's window -> predictions -> (all-gather) -> global alignment; returns the scene"""
         _, preds = pipe.reconstruct(video[:, :, my], stride=8, windows=[slice(0, 16, 1)], align=False,
                                     x_T_fn=lambda wi: torch.randn((1, 16, 16, H // 8, W // 8), device=dev,
                                                                   generator=torch.Generator(device=dev).manual_seed(123 + rank)))
-        p = preds[0]
-        if world > 1:
-            packed = torch.cat([p["pts3d"].reshape(-1), p["conf"].reshape(-1), p["inverse_depthmap"].reshape(-1),
-                                p["traj"].reshape(-1)])
-            allp = torch.empty(world * hw5, device=dev)
-            dist.all_gather_into_tensor(allp, packed)
-            preds = []
-            for r in range(world):
-                q = allp[r * hw5:(r + 1) * hw5]
-                n = 16 * H * W
-                preds.append({"pts3d": q[:3 * n].view(16, H, W, 3), "conf": q[3 * n:4 * n].view(16, H, W, 1),
-                              "inverse_depthmap": q[4 * n:5 * n].view(16, H, W, 1), "traj": q[5 * n:].view(16, 4, 4)})
+        preds = sharding.gather_predictions({rank: preds[0]}, world, 16, H, W)
         views = [[{"idx": (i,)} for i in range(w.start, w.stop)] for w in windows]
         with torch.enable_grad():
             scene = pipe.post_optimization(views, preds)
