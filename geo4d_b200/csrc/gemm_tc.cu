@@ -243,7 +243,9 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                   f = unpack_bf16x2(w.w); o[8 * j + 6] += f.x; o[8 * j + 7] += f.y;
                 }
               } else {
-                for (int j = 0; j < ncols; ++j) o[j] += __bfloat162float(rp[j]);
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < ncols) o[j] += __bfloat162float(rp[j]);
               }
             }
             if (args.out_fp32) {
@@ -253,7 +255,9 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < 8; ++j) o4[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
               } else {
-                for (int j = 0; j < ncols; ++j) op[j] = o[j];
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < ncols) op[j] = o[j];
               }
             } else {
               __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(args.out) + row * args.ldc + col0;
@@ -269,7 +273,9 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                   o4[j] = w;
                 }
               } else {
-                for (int j = 0; j < ncols; ++j) op[j] = __float2bfloat16(o[j]);
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < ncols) op[j] = __float2bfloat16(o[j]);
               }
             }
           }

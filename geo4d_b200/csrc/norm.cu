@@ -5,9 +5,9 @@
 //    Statistics are per (sample, group) over `rows_per_stat` consecutive rows: H*W rows for the
 //    per-frame norms of ResBlock / SpatialTransformer, T*H*W rows for the 5-D norms of
 //    TemporalConvBlock / TemporalTransformer (F.group_norm reduces over (C/G, T, H, W) there).
-//    Two passes: (1) fp32 sum / sum-of-squares per group with one atomicAdd pair per block and
-//    group; (2) y = x * scale[c] + shift[c] (+ SiLU) with scale/shift staged in shared memory.
-//    Algorithmic traffic: 2 reads + 1 write of the tensor (second read normally hits L2).
+//    Two passes: (1) fp32 sum / sum-of-squares per group, one partial per block (no atomics, so the
+//    result is deterministic); (2) y = x * scale[c] + shift[c] (+ SiLU) with scale/shift staged in
+//    shared memory.  Algorithmic traffic: 2 reads + 1 write of the tensor (second read normally hits L2).
 //  * LayerNorm over C per row: nn.LayerNorm at attention.py:229-231 (one warp per row, two-pass
 //    in registers).
 #include "common.cuh"
@@ -16,23 +16,39 @@
 namespace g4 {
 
 // ---------------------------------------------------------------------------------------------- GroupNorm
-// block = (C/8, ty): each thread owns a fixed 8-channel vector and strides over rows.
+// block = (C/8, ty): each thread owns a fixed 8-channel vector and strides over rows.  Per-block partial
+// {sum, sumsq} per group go to part[stat][block][32][2] (no atomics: deterministic); gn_apply sums the
+// partials of its statistic while it builds the per-channel scale/shift table.
 __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int C, int rows_per_stat,
-                                int rows_per_block, float* __restrict__ stats /*[S][32][2]*/) {
-  extern __shared__ float sm[];  // [2*C]
+                                int rows_per_block, float* __restrict__ part /*[S][nblk][32][2]*/) {
+  extern __shared__ float sm[];  // [ty][2*C] partials, then [2*C] totals in row 0
   const int s = blockIdx.y;
   const int row0 = blockIdx.x * rows_per_block;
   const int row1 = min(row0 + rows_per_block, rows_per_stat);
   const int vec = threadIdx.x;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const int nthr = blockDim.x * blockDim.y;
-  for (int i = tid; i < 2 * C; i += nthr) sm[i] = 0.f;
-  __syncthreads();
   float sum[8], sq[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { sum[j] = 0.f; sq[j] = 0.f; }
   const __nv_bfloat16* base = x + ((long long)s * rows_per_stat) * ld + vec * 8;
-  for (int r = row0 + threadIdx.y; r < row1; r += blockDim.y) {
+  const int step = blockDim.y;
+  int r = row0 + threadIdx.y;
+  // 4 independent 16-byte loads in flight per thread
+  for (; r + 3 * step < row1; r += 4 * step) {
+    uint4 w[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) w[u] = __ldg(reinterpret_cast<const uint4*>(base + (long long)(r + u * step) * ld));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float2 f;
+      f = unpack_bf16x2(w[u].x); sum[0] += f.x; sq[0] += f.x * f.x; sum[1] += f.y; sq[1] += f.y * f.y;
+      f = unpack_bf16x2(w[u].y); sum[2] += f.x; sq[2] += f.x * f.x; sum[3] += f.y; sq[3] += f.y * f.y;
+      f = unpack_bf16x2(w[u].z); sum[4] += f.x; sq[4] += f.x * f.x; sum[5] += f.y; sq[5] += f.y * f.y;
+      f = unpack_bf16x2(w[u].w); sum[6] += f.x; sq[6] += f.x * f.x; sum[7] += f.y; sq[7] += f.y * f.y;
+    }
+  }
+  for (; r < row1; r += step) {
     const uint4 w = __ldg(reinterpret_cast<const uint4*>(base + (long long)r * ld));
     float2 f;
     f = unpack_bf16x2(w.x); sum[0] += f.x; sq[0] += f.x * f.x; sum[1] += f.y; sq[1] += f.y * f.y;
@@ -40,26 +56,33 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long l
     f = unpack_bf16x2(w.z); sum[4] += f.x; sq[4] += f.x * f.x; sum[5] += f.y; sq[5] += f.y * f.y;
     f = unpack_bf16x2(w.w); sum[6] += f.x; sq[6] += f.x * f.x; sum[7] += f.y; sq[7] += f.y * f.y;
   }
+  float* mine = sm + (size_t)threadIdx.y * 2 * C;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    atomicAdd(&sm[vec * 8 + j], sum[j]);
-    atomicAdd(&sm[C + vec * 8 + j], sq[j]);
+    mine[vec * 8 + j] = sum[j];
+    mine[C + vec * 8 + j] = sq[j];
+  }
+  __syncthreads();
+  for (int c = tid; c < 2 * C; c += nthr) {
+    float a = 0.f;
+    for (int y = 0; y < (int)blockDim.y; ++y) a += sm[(size_t)y * 2 * C + c];
+    sm[c] = a;  // each column is read and written by exactly one thread
   }
   __syncthreads();
   const int cpg = C / 32;
-  if (tid < 32) {
-    float a = 0.f, b = 0.f;
-    for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) { a += sm[c]; b += sm[C + c]; }
-    atomicAdd(&stats[((long long)s * 32 + tid) * 2 + 0], a);
-    atomicAdd(&stats[((long long)s * 32 + tid) * 2 + 1], b);
+  if (tid < 64) {
+    const int g = tid & 31, which = tid >> 5;
+    float a = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) a += sm[which * C + c];
+    part[(((long long)s * gridDim.x + blockIdx.x) * 32 + g) * 2 + which] = a;
   }
 }
 
 __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long ld, __nv_bfloat16* __restrict__ y,
                                 long long ldy, int C, int rows_per_stat, int rows_per_block,
-                                const float* __restrict__ stats, const float* __restrict__ gamma,
+                                const float* __restrict__ part, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, int silu) {
-  extern __shared__ float sm[];  // scale[C], shift[C]
+  extern __shared__ float sm[];  // scale[C], shift[C], stats[64]
   const int s = blockIdx.y;
   const int row0 = blockIdx.x * rows_per_block;
   const int row1 = min(row0 + rows_per_block, rows_per_stat);
@@ -67,11 +90,19 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long l
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const int nthr = blockDim.x * blockDim.y;
   const int cpg = C / 32;
+  float* st = sm + 2 * C;
+  if (tid < 64) {
+    const int g = tid & 31, which = tid >> 5;
+    float a = 0.f;
+    for (int b = 0; b < (int)gridDim.x; ++b) a += part[(((long long)s * gridDim.x + b) * 32 + g) * 2 + which];
+    st[which * 32 + g] = a;
+  }
+  __syncthreads();
   const float inv_cnt = 1.0f / ((float)cpg * (float)rows_per_stat);
   for (int c = tid; c < C; c += nthr) {
     const int g = c / cpg;
-    const float mean = stats[((long long)s * 32 + g) * 2 + 0] * inv_cnt;
-    const float var = fmaxf(stats[((long long)s * 32 + g) * 2 + 1] * inv_cnt - mean * mean, 0.f);
+    const float mean = st[g] * inv_cnt;
+    const float var = fmaxf(st[32 + g] * inv_cnt - mean * mean, 0.f);
     const float rstd = rsqrtf(var + eps);
     const float sc = gamma[c] * rstd;
     sm[c] = sc;
@@ -83,23 +114,32 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long l
   for (int j = 0; j < 8; ++j) { sc[j] = sm[vec * 8 + j]; sh[j] = sm[C + vec * 8 + j]; }
   const __nv_bfloat16* xb = x + ((long long)s * rows_per_stat) * ld + vec * 8;
   __nv_bfloat16* yb = y + ((long long)s * rows_per_stat) * ldy + vec * 8;
-  for (int r = row0 + threadIdx.y; r < row1; r += blockDim.y) {
-    const uint4 w = __ldg(reinterpret_cast<const uint4*>(xb + (long long)r * ld));
-    float v[8];
-    float2 f;
-    f = unpack_bf16x2(w.x); v[0] = f.x; v[1] = f.y;
-    f = unpack_bf16x2(w.y); v[2] = f.x; v[3] = f.y;
-    f = unpack_bf16x2(w.z); v[4] = f.x; v[5] = f.y;
-    f = unpack_bf16x2(w.w); v[6] = f.x; v[7] = f.y;
+  const int step = blockDim.y;
+  for (int r0 = row0 + threadIdx.y; r0 < row1; r0 += 4 * step) {
+    uint4 w[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      v[j] = v[j] * sc[j] + sh[j];
-      if (silu) v[j] = silu_f(v[j]);
+    for (int u = 0; u < 4; ++u)
+      if (r0 + u * step < row1) w[u] = __ldg(reinterpret_cast<const uint4*>(xb + (long long)(r0 + u * step) * ld));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (r0 + u * step < row1) {
+        float v[8];
+        float2 f;
+        f = unpack_bf16x2(w[u].x); v[0] = f.x; v[1] = f.y;
+        f = unpack_bf16x2(w[u].y); v[2] = f.x; v[3] = f.y;
+        f = unpack_bf16x2(w[u].z); v[4] = f.x; v[5] = f.y;
+        f = unpack_bf16x2(w[u].w); v[6] = f.x; v[7] = f.y;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[j] = v[j] * sc[j] + sh[j];
+          if (silu) v[j] = silu_f(v[j]);
+        }
+        uint4 o;
+        o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+        o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(yb + (long long)(r0 + u * step) * ldy) = o;
+      }
     }
-    uint4 o;
-    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(yb + (long long)r * ldy) = o;
   }
 }
 
@@ -173,14 +213,32 @@ int device_sm_count();
 
 using namespace g4;
 
-extern "C" size_t geo4d_groupnorm_workspace_bytes(int num_stats) { return (size_t)num_stats * 32 * 2 * sizeof(float); }
+static void gn_launch_shape(int num_stats, int rows_per_stat, int C, int sms, dim3* block, dim3* grid,
+                            int* rows_per_block) {
+  const int vecs = C / 8;
+  int ty = 512 / vecs; if (ty < 1) ty = 1; if (ty > 32) ty = 32;
+  *block = dim3(vecs, ty);
+  int blocks_per_stat = (4 * sms + num_stats - 1) / num_stats;  // ~4 blocks per SM overall
+  int rpb = (rows_per_stat + blocks_per_stat - 1) / blocks_per_stat;
+  if (rpb < 8 * ty) rpb = 8 * ty;
+  blocks_per_stat = (rows_per_stat + rpb - 1) / rpb;
+  *rows_per_block = rpb;
+  *grid = dim3(blocks_per_stat, num_stats);
+}
+
+extern "C" size_t geo4d_groupnorm_workspace_bytes(int num_stats, int rows_per_stat, int C) {
+  if (num_stats < 1 || rows_per_stat < 1 || C < 8) return 0;
+  dim3 block, grid; int rpb;
+  gn_launch_shape(num_stats, rows_per_stat, C, 148, &block, &grid, &rpb);  // upper bound: fewer SMs -> fewer blocks
+  return (size_t)num_stats * grid.x * 64 * sizeof(float);
+}
 
 extern "C" int geo4d_groupnorm_silu(const void* x, int64_t ldx, void* y, int64_t ldy, int num_stats,
                                     int rows_per_stat, int C, const float* gamma, const float* beta, float eps,
                                     int apply_silu, void* workspace, size_t workspace_bytes, g4_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!x || !y || !gamma || !beta || !workspace) { set_last_error("groupnorm: null pointer"); return G4_ERR_BAD_ARG; }
-  if (C % 32 || C % 8 || C > 8 * 1024 || num_stats < 1 || rows_per_stat < 1) {
+  if (C % 32 || C % 8 || C > 8 * 1024 || num_stats < 1 || num_stats > 65535 || rows_per_stat < 1) {
     set_last_error("groupnorm: C=%d must be a multiple of 32 and 8 (<=8192); num_stats=%d rows=%d", C, num_stats,
                    rows_per_stat);
     return G4_ERR_BAD_ARG;
@@ -188,29 +246,28 @@ extern "C" int geo4d_groupnorm_silu(const void* x, int64_t ldx, void* y, int64_t
   if (ldx % 8 || ldy % 8 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) {
     set_last_error("groupnorm: x/y must be 16-byte aligned with ld multiple of 8"); return G4_ERR_BAD_ARG;
   }
-  const size_t need = geo4d_groupnorm_workspace_bytes(num_stats);
-  if (workspace_bytes < need) { set_last_error("groupnorm: workspace %zu < %zu", workspace_bytes, need); return G4_ERR_WORKSPACE; }
-  const int vecs = C / 8;
-  if (vecs > 1024) { set_last_error("groupnorm: C too large"); return G4_ERR_UNSUPPORTED; }
-  int ty = 512 / vecs; if (ty < 1) ty = 1; if (ty > 64) ty = 64;
-  dim3 block(vecs, ty);
-  // aim for ~4 blocks per SM overall, at least 4*ty rows per block
   const int sms = device_sm_count(); if (sms <= 0) return G4_ERR_CUDA;
-  int blocks_per_stat = (4 * sms + num_stats - 1) / num_stats;
-  int rows_per_block = (rows_per_stat + blocks_per_stat - 1) / blocks_per_stat;
-  if (rows_per_block < 4 * ty) rows_per_block = 4 * ty;
-  blocks_per_stat = (rows_per_stat + rows_per_block - 1) / rows_per_block;
-  dim3 grid(blocks_per_stat, num_stats);
-  const size_t smem = 2 * (size_t)C * sizeof(float);
-  cudaError_t e = cudaMemsetAsync(workspace, 0, need, stream);
-  if (e != cudaSuccess) { set_last_error("groupnorm: memset: %s", cudaGetErrorString(e)); return G4_ERR_CUDA; }
-  gn_stats_kernel<<<grid, block, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, C, rows_per_stat,
-                                                 rows_per_block, reinterpret_cast<float*>(workspace));
+  dim3 block, grid; int rows_per_block;
+  gn_launch_shape(num_stats, rows_per_stat, C, sms > 148 ? 148 : sms, &block, &grid, &rows_per_block);
+  const size_t need = (size_t)num_stats * grid.x * 64 * sizeof(float);
+  if (workspace_bytes < need) { set_last_error("groupnorm: workspace %zu < %zu", workspace_bytes, need); return G4_ERR_WORKSPACE; }
+  const size_t smem_stats = (size_t)block.y * 2 * C * sizeof(float);
+  const size_t smem_apply = (2 * (size_t)C + 64) * sizeof(float);
+  if (smem_stats > 48 * 1024) {
+    static bool attr = false;
+    if (!attr) {
+      cudaError_t e = cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      if (e != cudaSuccess) { set_last_error("groupnorm: smem attr: %s", cudaGetErrorString(e)); return G4_ERR_CUDA; }
+      attr = true;
+    }
+  }
+  gn_stats_kernel<<<grid, block, smem_stats, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, C, rows_per_stat,
+                                                       rows_per_block, reinterpret_cast<float*>(workspace));
   int rc = check_launch("gn_stats"); if (rc) return rc;
-  gn_apply_kernel<<<grid, block, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx,
-                                                 reinterpret_cast<__nv_bfloat16*>(y), ldy, C, rows_per_stat,
-                                                 rows_per_block, reinterpret_cast<const float*>(workspace), gamma, beta,
-                                                 eps, apply_silu);
+  gn_apply_kernel<<<grid, block, smem_apply, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx,
+                                                       reinterpret_cast<__nv_bfloat16*>(y), ldy, C, rows_per_stat,
+                                                       rows_per_block, reinterpret_cast<const float*>(workspace), gamma,
+                                                       beta, eps, apply_silu);
   return check_launch("gn_apply");
 }
 

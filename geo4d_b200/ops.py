@@ -149,11 +149,13 @@ def _s():
 _gn_ws = {}
 
 
-def _gn_workspace(device, num_stats: int) -> torch.Tensor:
-    need = num_stats * 64
+def _gn_workspace(device, num_stats: int, rows_per_stat: int, Cc: int) -> torch.Tensor:
+    f = lib().geo4d_groupnorm_workspace_bytes
+    f.restype = C.c_size_t
+    need = int(f(num_stats, rows_per_stat, Cc)) // 4
     ws = _gn_ws.get(device)
     if ws is None or ws.numel() < need:
-        ws = torch.empty(max(need, 64 * 64), device=device, dtype=torch.float32)
+        ws = torch.empty(max(need, 1 << 18), device=device, dtype=torch.float32)
         _gn_ws[device] = ws
     return ws
 
@@ -165,7 +167,7 @@ def groupnorm(x: torch.Tensor, num_stats: int, rows_per_stat: int, gamma: torch.
     Cc = x.shape[1]
     if out is None:
         out = torch.empty((x.shape[0], Cc), device=x.device, dtype=torch.bfloat16)
-    ws = workspace if workspace is not None else _gn_workspace(x.device, num_stats)
+    ws = workspace if workspace is not None else _gn_workspace(x.device, num_stats, rows_per_stat, Cc)
     check(lib().geo4d_groupnorm_silu(_vp(x), C.c_int64(x.stride(0)), _vp(out), C.c_int64(out.stride(0)),
                                      num_stats, rows_per_stat, Cc, _vp(gamma), _vp(beta), C.c_float(eps),
                                      1 if silu else 0, _vp(ws), C.c_size_t(ws.numel() * 4), _s()),

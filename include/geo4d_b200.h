@@ -111,7 +111,7 @@ int geo4d_temporal_attention(const void* q, const void* k, const void* v, int64_
 
 /* GroupNorm(32) [+SiLU] over `rows_per_stat` consecutive rows per statistic (basics.py:76-87,
  * openaimodel3d.py:151-155,175-180,256-266; attention.py:265,331; ae_modules.py:14-15). */
-size_t geo4d_groupnorm_workspace_bytes(int num_stats);
+size_t geo4d_groupnorm_workspace_bytes(int num_stats, int rows_per_stat, int C);
 int geo4d_groupnorm_silu(const void* x, int64_t ldx, void* y, int64_t ldy, int num_stats, int rows_per_stat,
                          int C, const float* gamma, const float* beta, float eps, int apply_silu,
                          void* workspace, size_t workspace_bytes, g4_stream_t stream);

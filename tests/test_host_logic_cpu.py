@@ -1,0 +1,96 @@
+"""CPU: host-side logic of the product that needs no GPU -- schedule tables (bit-identical to the oracle, which is
+pinned to the reference), window slicing, config aliasing, GEGLU interleave, M-tile picker."""
+import json
+import os
+
+import numpy as np
+import torch
+
+from geo4d_b200 import schedule as ps
+from oracle import ddim as od
+
+
+def test_schedule_tables_bit_identical_to_oracle():
+    bufs = ps.register_schedule_buffers(1000, 0.00085, 0.012, "linear", True)
+    sch = od.Schedule.geo4d()
+    assert np.array_equal(bufs["betas"], sch.betas)
+    assert np.array_equal(bufs["alphas_cumprod"], sch.alphas_cumprod)
+    assert np.array_equal(bufs["sqrt_alphas_cumprod"], sch.sqrt_alphas_cumprod)
+    assert np.array_equal(bufs["sqrt_one_minus_alphas_cumprod"], sch.sqrt_one_minus_alphas_cumprod)
+    assert np.array_equal(ps.make_scale_arr(), sch.scale_arr)
+    for S in (2, 5, 50):
+        mine = ps.DDIMTables(bufs["alphas_cumprod"], ps.make_scale_arr(), S, "uniform_trailing", 0.0)
+        ref = od.make_ddim_tables(sch, S)
+        assert np.array_equal(mine.timesteps, ref.timesteps)
+        assert np.array_equal(mine.alphas.astype(np.float32), ref.alphas)
+        assert np.array_equal(np.asarray(mine.alphas_prev, np.float32), ref.alphas_prev)
+        assert np.array_equal(mine.scale, ref.scale) and np.array_equal(mine.scale_prev, ref.scale_prev)
+
+
+def test_step_coefficients_reproduce_oracle_update():
+    """geo4d_ddim_step's {sa, s1, rescale, sqrt(a_prev), dir, sigma} rows give the oracle's p_sample_ddim."""
+    bufs = ps.register_schedule_buffers(1000, 0.00085, 0.012, "linear", True)
+    sch = od.Schedule.geo4d()
+    S = 5
+    tab = ps.DDIMTables(bufs["alphas_cumprod"], ps.make_scale_arr(), S, "uniform_trailing", 0.0)
+    coef = tab.step_coefficients(bufs["sqrt_alphas_cumprod"], bufs["sqrt_one_minus_alphas_cumprod"])
+    otab = od.make_ddim_tables(sch, S)
+    g = torch.Generator().manual_seed(0)
+    x, v = torch.randn(64, generator=g), torch.randn(64, generator=g)
+    for i in range(S):
+        index = S - 1 - i
+        ref, ref_x0 = od.ddim_step_v(x, v, sch, otab, index)
+        sa, s1, rs, sap, dr, sg = [torch.tensor(float(c)) for c in coef[i]]
+        e_t = sa * v + s1 * x
+        x0 = (sa * x - s1 * v) * rs
+        assert torch.allclose(x0, ref_x0, rtol=0, atol=1e-6)
+        assert torch.allclose(sap * x0 + dr * e_t, ref, rtol=0, atol=1e-6)
+    # first step: abar_999 = 0  =>  pred_x0 = -v * rescale, e_t = x
+    assert coef[0][0] == 0.0 and coef[0][1] == 1.0
+
+
+def test_sliding_windows_match_reference_rule():
+    from geo4d_b200.pipeline import sliding_windows
+    assert [(s.start, s.stop) for s in sliding_windows(50, 8)] == [(0, 16), (8, 24), (16, 32), (24, 40), (32, 48), (34, 50)]
+    assert [(s.start, s.stop) for s in sliding_windows(16, 8)] == [(0, 16)]
+    assert len(sliding_windows(264, 8)) == 32
+
+
+def test_config_aliases_resolve_reference_targets():
+    from geo4d_b200.config import get_obj_from_str, load_yaml
+    from geo4d_b200.unet import UNetModel
+    from geo4d_b200.vae import AutoencoderKL
+    assert get_obj_from_str("lvdm.modules.networks.openaimodel3d.UNetModel") is UNetModel
+    assert get_obj_from_str("lvdm.models.autoencoder.AutoencoderKL") is AutoencoderKL
+    cfg = load_yaml(os.path.join(os.path.dirname(os.path.dirname(__file__)), "configs", "inference_geo4d.yaml"))
+    assert cfg["model"]["params"]["unet_config"]["params"]["model_channels"] == 320
+    assert cfg["postprocess"]["n_iter"] == 500
+
+
+def test_geglu_interleave_and_tile_picker():
+    from geo4d_b200.unet import _interleave32
+    from geo4d_b200.ops import pick_box
+    a = torch.arange(64).float()[:, None]
+    b = 100 + torch.arange(64).float()[:, None]
+    w = _interleave32(a, b)[:, 0]
+    assert w[:32].tolist() == list(range(32)) and w[32:64].tolist() == [100 + i for i in range(32)]
+    assert w[64:96].tolist() == list(range(32, 64))
+    for (W, H, N) in [(64, 40, 16), (32, 20, 16), (16, 10, 16), (8, 5, 16), (512, 320, 4), (2560, 16, 1)]:
+        bw, bh, bn = pick_box(W, H, N)
+        assert bw * bh * bn <= 128 and bw <= W and bh <= H and bn <= N
+    assert pick_box(64, 40, 16) == (64, 2, 1) and pick_box(8, 5, 16) == (8, 1, 16)
+
+
+def test_full_model_state_dict_layout(golden_dir):
+    """LatentVisualDiffusion exposes model.diffusion_model.* / first_stage_model.* + the schedule buffers."""
+    from geo4d_b200.config import instantiate_from_config, load_yaml
+    cfg = load_yaml(os.path.join(os.path.dirname(os.path.dirname(__file__)), "configs", "inference_geo4d.yaml"))
+    with torch.device("meta"):
+        m = instantiate_from_config(cfg["model"])
+    keys = set(m.state_dict().keys())
+    unet = json.load(open(os.path.join(golden_dir, "unet_full_keys.json")))
+    assert all(("model.diffusion_model." + k) in keys for k in unet)
+    for b in ("betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod", "scale_arr",
+              "sqrt_one_minus_alphas_cumprod", "posterior_variance", "posterior_mean_coef1"):
+        assert b in keys
+    assert m.scale_arr.shape[0] == 1400 and m.num_timesteps == 1000 and m.parameterization == "v"
