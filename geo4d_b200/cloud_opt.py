@@ -14,8 +14,10 @@ Same constructor arguments, `compute_global_alignment(init='group', niter, sched
   pose-graph terms) stays in torch autograd on tensors of a few hundred floats, driven by the matrix-form
   gradients the kernel reduces, and the whole iteration is replayed from a CUDA graph (two graphs:
   before / after `depth_traj_start_iter`);
-* like the reference, the shift/focal Levenberg-Marquardt solve (scipy) and the per-frame RANSAC-PnP (cv2)
-  of the initialisation run on the host (SURVEY.md 8(f) N2 ports them next).
+* the initialisation solvers the reference runs on the CPU -- the shift/focal least-squares fit (scipy LM) and
+  the per-frame RANSAC-PnP (cv2, SQPnP) -- reduce their per-pixel sums on the GPU (geo4d_shift_focal_sums,
+  geo4d_pnp_moments) and solve only 1-D / 9x9 problems on the host (init_solvers.py); set
+  GEO4D_INIT_SOLVERS=host to call scipy / cv2 exactly like the reference (1.5-2 s per frame at 320x512).
 """
 from __future__ import annotations
 
@@ -335,39 +337,49 @@ class LightPointCloudGroupOptimizer(nn.Module):
         dev = self.device
         pred = self._stacked_pred_all.view(G, gs, HW, 3)
         conf = self._weight_all.view(G, gs, HW)
+        host_solvers = os.environ.get("GEO4D_INIT_SOLVERS", "gpu") == "host"  # cv2 / scipy exactly like the reference
         try:
-            focal_group = isv.focal_per_group(pred[:, 0].reshape(G, H, W, 3).cpu(), conf[:, 0].reshape(G, H, W).cpu())
+            if host_solvers:
+                focal_group = isv.focal_per_group(pred[:, 0].reshape(G, H, W, 3).cpu(), conf[:, 0].reshape(G, H, W).cpu())
+            else:
+                focal_group = isv.gpu_focal_per_group(ops, pred[:, 0].contiguous(), conf[:, 0].contiguous(), H, W)
             if not all(math.isfinite(f) for f in focal_group):
                 raise ValueError("non-finite focal")
         except Exception:
-            # same fallback as align_group_prefix (init_im_poses.py:272-278): focal search by RANSAC-PnP on the
-            # first frame, shared by all windows
+            # same fallback as align_group_prefix (init_im_poses.py:272-278): focal search by PnP on the first
+            # frame, shared by all windows
             if self.verbose:
                 print("Error in computing focal length")
-            res = isv.fast_pnp(pred[0, 0].reshape(H, W, 3).cpu().numpy(), None,
-                               (conf[0, 0] > 0.5).reshape(H, W).cpu().numpy(), niter_PnP)
-            focal_group = [res[0] if res else float(max(H, W))] * G
+            tmp_f, tmp_p = [None], [None]
+            isv.gpu_fast_pnp_frames(ops, pred[0, 0:1].contiguous(), conf[0, 0:1].contiguous(), H, W,
+                                    lambda k, img: None, tmp_f, tmp_p, [0], niter_PnP)
+            focal_group = [tmp_f[0] if tmp_f[0] else float(max(H, W))] * G
         pts3d = torch.zeros(N, HW, 3, device=dev)
         conf_list = torch.zeros(N, HW, device=dev)
         im_poses: List[Optional[np.ndarray]] = [None] * N
         im_focals: List[Optional[float]] = [None] * N
         done = set()
 
-        def pnp_frames(frame_ids, pts_cpu, msk_cpu, first_focal_of):
-            for k, img in enumerate(frame_ids):
-                tf = first_focal_of(k, img)
-                res = isv.fast_pnp(pts_cpu[k], tf, msk_cpu[k], niter_PnP)
-                if res:
-                    im_focals[img], im_poses[img] = res
-                if im_poses[img] is None:
-                    im_poses[img] = np.eye(4)
+        def pnp_frames(frame_ids, pts_gpu, conf_gpu, first_focal_of):
+            """per-frame pose + focal (fast_pnp, init_im_poses.py:824-865)"""
+            if host_solvers:
+                pts_cpu = pts_gpu.reshape(-1, H, W, 3).cpu().numpy()
+                msk_cpu = (conf_gpu > 0.5).reshape(-1, H, W).cpu().numpy()
+                for k, img in enumerate(frame_ids):
+                    res = isv.fast_pnp(pts_cpu[k], first_focal_of(k, img), msk_cpu[k], niter_PnP)
+                    if res:
+                        im_focals[img], im_poses[img] = res
+                    if im_poses[img] is None:
+                        im_poses[img] = np.eye(4)
+            else:
+                isv.gpu_fast_pnp_frames(ops, pts_gpu.contiguous(), conf_gpu.contiguous(), H, W, first_focal_of,
+                                        im_focals, im_poses, frame_ids, niter_PnP)
 
         g0 = self.groups[0]
         im_focals[g0[0]] = focal_group[0]
         pts3d[g0] = pred[0]
         conf_list[g0] = conf[0]
-        pnp_frames(g0, pred[0].reshape(gs, H, W, 3).cpu().numpy(), (conf[0] > 0.5).reshape(gs, H, W).cpu().numpy(),
-                   lambda k, img: im_focals[img - 1] if img != 0 else im_focals[img])
+        pnp_frames(g0, pred[0], conf[0], lambda k, img: im_focals[img - 1] if img != 0 else im_focals[img])
         done.update(g0)
         for i in range(1, G):
             group = self.groups[i]
@@ -386,8 +398,7 @@ class LightPointCloudGroupOptimizer(nn.Module):
                 P = np.eye(4)
                 P[:3, :3], P[:3, 3] = R, T
                 im_poses[group[0]] = P
-            pnp_frames(group, new_pts.reshape(gs, H, W, 3).cpu().numpy(),
-                       (conf[i] > 0.5).reshape(gs, H, W).cpu().numpy(),
+            pnp_frames(group, new_pts, conf[i],
                        lambda k, img, fg=focal_group[i]: fg if k == 0 else im_focals[img - 1])
             done.update(group)
         im_poses_np = np.stack(im_poses)
@@ -408,6 +419,10 @@ class LightPointCloudGroupOptimizer(nn.Module):
         self.im_depthmaps.data.copy_(depth.log().nan_to_num(neginf=0))
         for i in range(N):
             self._set_pose(self.im_poses, i, im_poses_np[i][:3, :3], im_poses_np[i][:3, 3])
+        # (the reference assumes every frame got a focal from PnP; a frame whose PnP failed inherits its neighbour's)
+        for i in range(N):
+            if im_focals[i] is None or not math.isfinite(im_focals[i]) or im_focals[i] <= 0:
+                im_focals[i] = im_focals[i - 1] if i > 0 and im_focals[i - 1] else float(max(H, W))
         self.im_focals.data[:] = self.focal_break * math.log(sum(im_focals) / N)
         self._init_im_focals = im_focals
 

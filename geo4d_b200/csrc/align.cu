@@ -340,6 +340,98 @@ __global__ void delta125_kernel(const float* __restrict__ x, const float* __rest
   block_reduce_atomic<2>(a, out + g * 2);
 }
 
+
+// ---------------------------------------------------------------------------------------------- PnP moments
+// Reductions of the SQPnP normal equations (Terzakis & Lourakis 2020, the solver behind
+// cv2.solvePnPRansac(flags=SOLVEPNP_SQPNP) as called by fast_pnp, init_im_poses.py:824-865).  With pixel
+// offsets (du, dv) = (u - cx, v - cy), r2 = du^2 + dv^2 and world point m, every entry of sum Q, sum Q A and
+// sum A^T Q A is (1/f)^k times one of
+//   out[0..4)   = { n, sum du, sum dv, sum r2 }
+//   out[4..16)  = { sum m, sum du m, sum dv m, sum r2 m }                       (3 each)
+//   out[16..40) = { sum m m^T, sum du m m^T, sum dv m m^T, sum r2 m m^T }        (6 unique each: xx xy xz yy yz zz)
+//   out[40]     = number of points used
+// so ONE pass serves every tentative focal.  With `gate` (per (frame, candidate) world-to-camera [R|t] and f)
+// only points with conf > 0.5, positive depth and reprojection error < thr pixels contribute: this is the
+// consensus set of the RANSAC stage, re-fitted by the same solver (what OpenCV does after RANSAC).
+__global__ void __launch_bounds__(256)
+pnp_moments_kernel(const float* __restrict__ pts, const float* __restrict__ conf, int HW, int W, float cx, float cy,
+                   const float* __restrict__ gate /*[F][C][13] or null*/, int C, float thr2,
+                   double* __restrict__ out /*[F][C][41]*/) {
+  const int f = blockIdx.y, c = blockIdx.z;
+  float acc[41];
+#pragma unroll
+  for (int i = 0; i < 41; ++i) acc[i] = 0.f;
+  float G[13];
+  if (gate) {
+#pragma unroll
+    for (int i = 0; i < 13; ++i) G[i] = gate[((long long)f * C + c) * 13 + i];
+  }
+  const float* P = pts + (long long)f * HW * 3;
+  const float* Cf = conf + (long long)f * HW;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+    if (!(Cf[p] > 0.5f)) continue;
+    const float X = P[3 * p], Y = P[3 * p + 1], Z = P[3 * p + 2];
+    const float u = (float)(p % W), v = (float)(p / W);
+    if (gate) {
+      const float xc = G[0] * X + G[1] * Y + G[2] * Z + G[3];
+      const float yc = G[4] * X + G[5] * Y + G[6] * Z + G[7];
+      const float zc = G[8] * X + G[9] * Y + G[10] * Z + G[11];
+      if (!(zc > 0.f)) continue;
+      const float eu = u - (G[12] * xc / zc + cx), ev = v - (G[12] * yc / zc + cy);
+      if (!(eu * eu + ev * ev < thr2)) continue;
+    }
+    const float du = u - cx, dv = v - cy, r2 = du * du + dv * dv;
+    const float mm[6] = {X * X, X * Y, X * Z, Y * Y, Y * Z, Z * Z};
+    acc[0] += 1.f; acc[1] += du; acc[2] += dv; acc[3] += r2;
+    acc[4] += X; acc[5] += Y; acc[6] += Z;
+    acc[7] += du * X; acc[8] += du * Y; acc[9] += du * Z;
+    acc[10] += dv * X; acc[11] += dv * Y; acc[12] += dv * Z;
+    acc[13] += r2 * X; acc[14] += r2 * Y; acc[15] += r2 * Z;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      acc[16 + k] += mm[k];
+      acc[22 + k] += du * mm[k];
+      acc[28 + k] += dv * mm[k];
+      acc[34 + k] += r2 * mm[k];
+    }
+    acc[40] += 1.f;
+  }
+  block_reduce_atomic<41>(acc, out + ((long long)f * C + c) * 41);
+}
+
+// Shift / focal fit of point_map_to_depth (utils/geometry.py:162-270): for a trial z-shift s per window the
+// reference minimises sum |f p - uv|^2 with p = xy / (z + s) and the optimal f = S1 / S2, S1 = sum p.uv,
+// S2 = sum |p|^2.  out[g] = { S1, S2, dS1/ds, dS2/ds, sum |uv|^2, n } over pixels with conf > 0.5.
+__global__ void shift_focal_sums_kernel(const float* __restrict__ pts, const float* __restrict__ conf, int HW, int W,
+                                        int H, const float* __restrict__ shift, float zoff,
+                                        double* __restrict__ out) {
+  const int g = blockIdx.y;
+  const float s = shift[g];
+  const float ar = (float)W / (float)H;
+  const float sx = ar / sqrtf(1.f + ar * ar), sy = 1.f / sqrtf(1.f + ar * ar);
+  float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const float* P = pts + (long long)g * HW * 3;
+  const float* Cf = conf + (long long)g * HW;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+    if (!(Cf[p] > 0.5f)) continue;
+    // image_plane_uv: linspace(-span*(n-1)/n, span*(n-1)/n, n)
+    const int iu = p % W, iv = p / W;
+    const float uu = W > 1 ? sx * (float)(W - 1) / (float)W * (2.f * (float)iu / (float)(W - 1) - 1.f) : 0.f;
+    const float vv = H > 1 ? sy * (float)(H - 1) / (float)H * (2.f * (float)iv / (float)(H - 1) - 1.f) : 0.f;
+    const float X = P[3 * p], Y = P[3 * p + 1], Z = P[3 * p + 2] + zoff;
+    const float iz = 1.0f / (Z + s);
+    const float px = X * iz, py = Y * iz;
+    const float dot = px * uu + py * vv, n2 = px * px + py * py;
+    a[0] += dot;
+    a[1] += n2;
+    a[2] -= dot * iz;        // d(p.uv)/ds
+    a[3] -= 2.f * n2 * iz;   // d|p|^2/ds
+    a[4] += uu * uu + vv * vv;
+    a[5] += 1.f;
+  }
+  block_reduce_atomic<6>(a, out + g * 6);
+}
+
 int device_sm_count();
 
 static inline int blocks_for(long long n, int cap) {
@@ -451,4 +543,36 @@ extern "C" int geo4d_delta125(const float* x, const float* y, const float* w, in
   dim3 grid(bx, G);
   delta125_kernel<<<grid, 256, 0, stream>>>(x, y, w, n_per_group, st, st_stride, out);
   return check_launch("delta125");
+}
+
+extern "C" int geo4d_pnp_moments(const float* pts, const float* conf, int F, int HW, int W, float cx, float cy,
+                                 const float* gate, int C, float thr_px, double* out, g4_stream_t stream_) {
+  G4_STREAM;
+  if (!pts || !conf || !out || F < 1 || F > 65535 || C < 1 || C > 65535) { set_last_error("pnp_moments: bad args"); return G4_ERR_BAD_ARG; }
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(double) * 41 * F * C, stream);
+  if (e != cudaSuccess) { set_last_error("pnp_moments: memset: %s", cudaGetErrorString(e)); return G4_ERR_CUDA; }
+  const int sms = device_sm_count(); if (sms <= 0) return G4_ERR_CUDA;
+  int bx = (2 * sms + F * C - 1) / (F * C);
+  const int maxbx = (HW + 255) / 256;
+  if (bx > maxbx) bx = maxbx;
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, F, C);
+  pnp_moments_kernel<<<grid, 256, 0, stream>>>(pts, conf, HW, W, cx, cy, gate, C, thr_px * thr_px, out);
+  return check_launch("pnp_moments");
+}
+
+extern "C" int geo4d_shift_focal_sums(const float* pts, const float* conf, int G, int HW, int W, int H,
+                                      const float* shift, float zoff, double* out, g4_stream_t stream_) {
+  G4_STREAM;
+  if (!pts || !conf || !shift || !out || G < 1 || G > 65535) { set_last_error("shift_focal_sums: bad args"); return G4_ERR_BAD_ARG; }
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(double) * 6 * G, stream);
+  if (e != cudaSuccess) { set_last_error("shift_focal_sums: memset: %s", cudaGetErrorString(e)); return G4_ERR_CUDA; }
+  const int sms = device_sm_count(); if (sms <= 0) return G4_ERR_CUDA;
+  int bx = (2 * sms + G - 1) / G;
+  const int maxbx = (HW + 255) / 256;
+  if (bx > maxbx) bx = maxbx;
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, G);
+  shift_focal_sums_kernel<<<grid, 256, 0, stream>>>(pts, conf, HW, W, H, shift, zoff, out);
+  return check_launch("shift_focal_sums");
 }

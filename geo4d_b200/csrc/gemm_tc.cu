@@ -4,7 +4,8 @@
 //
 //   warp 0 lane 0 : TMA producer   (4-D activation box + 3-D weight box per k-step, SWIZZLE_128B)
 //   warp 1 lane 0 : tcgen05.mma issuer (M=128, N=BLOCK_N, K=16 per instruction; fp32 accum in TMEM)
-//   warps 2..5    : epilogue (tcgen05.ld -> bias / row-bias / SiLU / GEGLU / residual -> bf16|fp32 store)
+//   warps 2..9    : epilogue (tcgen05.ld -> bias / row-bias / SiLU / GEGLU / residual -> bf16|fp32 store);
+//                   two warps per TMEM lane quadrant, additive terms staged in smem ahead of the MMAs
 //
 // The 3x3 / temporal taps are NOT im2col'ed: each tap is one more set of k-steps whose TMA box is
 // shifted by (dx, dy); the TMA unit zero-fills the out-of-bounds halo, so the activation is read
@@ -45,11 +46,11 @@ struct GemmCfg {
   static constexpr int B_BYTES = BLOCK_N * 64 * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 160 ? 5 : 6);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2048 /*bias*/;
 };
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const GemmArgs args) {
   using Cfg = GemmCfg<BLOCK_N>;
@@ -62,6 +63,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tfull = bars + 2 * STAGES;      // [2]
   uint64_t* tempty = bars + 2 * STAGES + 2; // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* s_bias = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);  // [2][256]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -75,7 +77,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);
+      mbar_init(&tempty[a], 8);
     }
     fence_barrier_init();
   }
@@ -148,7 +150,11 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     __syncwarp();
   } else {
+    // ---- epilogue: 8 warps; warps e and e+4 share a TMEM lane quadrant and split its 32-column chunks
+    const int e = warp - 2;
     const int q = warp & 3;            // TMEM lane quadrant this warp may access
+    const int half = e >> 2;           // chunk parity handled by this warp
+    const int et = threadIdx.x - 64;   // 0..255 among the epilogue threads
     const int r = q * 32 + lane;       // accumulator row handled by this thread
     const int rows_in_tile = args.box_w * args.box_h * args.box_n;
     int it = 0;
@@ -157,21 +163,50 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t acc_phase = (it >> 1) & 1;
       const int nt = tile % args.n_tiles;
       const int mt = tile / args.n_tiles;
-      const int x = (mt % args.tiles_x) * args.box_w + (r % args.box_w);
-      const int y = ((mt / args.tiles_x) % args.tiles_y) * args.box_h + ((r / args.box_w) % args.box_h);
-      const int n = (mt / (args.tiles_x * args.tiles_y)) * args.box_n + r / (args.box_w * args.box_h);
+      const int x0 = (mt % args.tiles_x) * args.box_w;
+      const int y0 = ((mt / args.tiles_x) % args.tiles_y) * args.box_h;
+      const int n0 = (mt / (args.tiles_x * args.tiles_y)) * args.box_n;
+      const int x = x0 + (r % args.box_w);
+      const int y = y0 + ((r / args.box_w) % args.box_h);
+      const int n = n0 + r / (args.box_w * args.box_h);
       const bool row_ok = (r < rows_in_tile) && (x < args.W) && (y < args.H) && (n < args.N);
       const long long row = ((long long)n * args.H + y) * args.W + x;
+      const int col_base = nt * BLOCK_N;
+
+      // Stage the per-column additive terms (bias + the emb row of this tile) in shared memory while the
+      // MMAs of this tile are still running: the epilogue then never waits on a global load for them.
+      float* sb = s_bias + acc * 256;
+      bool rb_in_smem = false;
+      {
+        long long rb_row = 0;
+        if (args.row_bias) {
+          const long long first = ((long long)n0 * args.H + y0) * args.W + x0;
+          const int nl = min(n0 + args.box_n, args.N) - 1, yl = min(y0 + args.box_h, args.H) - 1,
+                    xl = min(x0 + args.box_w, args.W) - 1;
+          const long long last = ((long long)nl * args.H + yl) * args.W + xl;
+          rb_row = first / args.rows_per_bias;
+          rb_in_smem = (last / args.rows_per_bias) == rb_row;
+        }
+        if (et < BLOCK_N) {
+          const int col = col_base + et;
+          float bv = 0.f;
+          if (col < args.n_out) {
+            if (args.bias) bv = __ldg(args.bias + col);
+            if (rb_in_smem) bv += __ldg(args.row_bias + rb_row * args.row_bias_ld + col);
+          }
+          sb[et] = bv;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
 
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
-      const int col_base = nt * BLOCK_N;
 
       if (args.act == G4_ACT_GEGLU) {
         // column blocks alternate [32 value | 32 gate]; stored width is n_out/2
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 64; ++c) {
+        for (int c = half; c < BLOCK_N / 64; c += 2) {
           uint32_t v[32], g[32];
           tmem_ld32(t_row + c * 64, v);
           tmem_ld32(t_row + c * 64 + 32, g);
@@ -180,12 +215,18 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const int ocol0 = col0 >> 1;                  // stored column
           if (row_ok && col0 < args.n_out) {
             float o[32];
+            const float4* b4 = reinterpret_cast<const float4*>(sb + c * 64);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float a = __uint_as_float(v[j]) * args.alpha;
-              float b = __uint_as_float(g[j]) * args.alpha;
-              if (args.bias) { a += __ldg(args.bias + col0 + j); b += __ldg(args.bias + col0 + 32 + j); }
-              o[j] = a * gelu_erf_f(b);
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 ba = b4[j4], bg = b4[8 + j4];
+              const float bav[4] = {ba.x, ba.y, ba.z, ba.w}, bgv[4] = {bg.x, bg.y, bg.z, bg.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int j = 4 * j4 + k;
+                const float a = fmaf(__uint_as_float(v[j]), args.alpha, bav[k]);
+                const float b = fmaf(__uint_as_float(g[j]), args.alpha, bgv[k]);
+                o[j] = a * gelu_erf_f(b);
+              }
             }
             __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(args.out) + row * args.ldc + ocol0;
             uint4* o4 = reinterpret_cast<uint4*>(op);
@@ -202,22 +243,39 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       } else {
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 32; ++c) {
+        for (int c = half; c < BLOCK_N / 32; c += 2) {
+          const int col0 = col_base + c * 32;
+          const bool active = row_ok && col0 < args.n_out;
+          const int ncols = min(32, args.n_out - col0);
+          const bool vec_ok = (ncols == 32);
           uint32_t v[32];
           tmem_ld32(t_row + c * 32, v);
-          tmem_ld_wait();
-          const int col0 = col_base + c * 32;
-          if (row_ok && col0 < args.n_out) {
-            const int ncols = min(32, args.n_out - col0);
-            float o[32];
+          // residual loads are issued before waiting on the TMEM load so both latencies overlap
+          uint4 rr[4];
+          const __nv_bfloat16* rp = nullptr;
+          bool res_vec = false;
+          if (active && args.residual) {
+            rp = reinterpret_cast<const __nv_bfloat16*>(args.residual) + row * args.ldr + col0;
+            res_vec = vec_ok && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0);
+            if (res_vec) {
+              const uint4* r4 = reinterpret_cast<const uint4*>(rp);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]) * args.alpha;
-            if (args.bias) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < ncols) o[j] += __ldg(args.bias + col0 + j);
+              for (int j = 0; j < 4; ++j) rr[j] = r4[j];
             }
-            if (args.row_bias) {
+          }
+          tmem_ld_wait();
+          if (active) {
+            float o[32];
+            const float4* b4 = reinterpret_cast<const float4*>(sb + c * 32);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 bb = b4[j4];
+              o[4 * j4 + 0] = fmaf(__uint_as_float(v[4 * j4 + 0]), args.alpha, bb.x);
+              o[4 * j4 + 1] = fmaf(__uint_as_float(v[4 * j4 + 1]), args.alpha, bb.y);
+              o[4 * j4 + 2] = fmaf(__uint_as_float(v[4 * j4 + 2]), args.alpha, bb.z);
+              o[4 * j4 + 3] = fmaf(__uint_as_float(v[4 * j4 + 3]), args.alpha, bb.w);
+            }
+            if (args.row_bias && !rb_in_smem) {  // tile straddles two embedding rows: per-thread loads
               const float* rb = args.row_bias + (row / args.rows_per_bias) * args.row_bias_ld + col0;
 #pragma unroll
               for (int j = 0; j < 32; ++j)
@@ -227,20 +285,15 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
               for (int j = 0; j < 32; ++j) o[j] = silu_f(o[j]);
             }
-            const bool vec_ok = (ncols == 32);
             if (args.residual) {
-              const __nv_bfloat16* rp =
-                  reinterpret_cast<const __nv_bfloat16*>(args.residual) + row * args.ldr + col0;
-              if (vec_ok && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
-                const uint4* r4 = reinterpret_cast<const uint4*>(rp);
+              if (res_vec) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  uint4 w = r4[j];
                   float2 f;
-                  f = unpack_bf16x2(w.x); o[8 * j + 0] += f.x; o[8 * j + 1] += f.y;
-                  f = unpack_bf16x2(w.y); o[8 * j + 2] += f.x; o[8 * j + 3] += f.y;
-                  f = unpack_bf16x2(w.z); o[8 * j + 4] += f.x; o[8 * j + 5] += f.y;
-                  f = unpack_bf16x2(w.w); o[8 * j + 6] += f.x; o[8 * j + 7] += f.y;
+                  f = unpack_bf16x2(rr[j].x); o[8 * j + 0] += f.x; o[8 * j + 1] += f.y;
+                  f = unpack_bf16x2(rr[j].y); o[8 * j + 2] += f.x; o[8 * j + 3] += f.y;
+                  f = unpack_bf16x2(rr[j].z); o[8 * j + 4] += f.x; o[8 * j + 5] += f.y;
+                  f = unpack_bf16x2(rr[j].w); o[8 * j + 6] += f.x; o[8 * j + 7] += f.y;
                 }
               } else {
 #pragma unroll
@@ -312,7 +365,7 @@ static int launch_tap_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const
   }
   const int total = a.tiles_x * a.tiles_y * a.tiles_n * a.n_tiles;
   const int grid = total < num_sms ? total : num_sms;
-  tap_gemm_kernel<BLOCK_N><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, a);
+  tap_gemm_kernel<BLOCK_N><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, a);
   return check_launch("tap_gemm");
 }
 

@@ -85,3 +85,209 @@ def fast_pnp(pts3d: np.ndarray, focal: Optional[float], msk: np.ndarray, niter_P
     w2c[:3, :3] = cv2.Rodrigues(R)[0]
     w2c[:3, 3] = np.asarray(T).ravel()
     return bf, np.linalg.inv(w2c)
+
+
+# =============================================================================== GPU-reduced variants
+# The per-pixel work (41 SQPnP moments per frame, shift/focal sums per window) is reduced on the GPU
+# (geo4d_pnp_moments / geo4d_shift_focal_sums); only 9x9 / 1-D problems are solved here, in fp64.
+
+def moments_numpy(pts: np.ndarray, mask: np.ndarray, cx: float, cy: float) -> np.ndarray:
+    """Reference (host) computation of the 41 moments of geo4d_pnp_moments, for tests."""
+    H, W, _ = pts.shape
+    v, u = np.mgrid[:H, :W]
+    m = pts[mask].astype(np.float64)
+    du, dv = (u[mask] - cx).astype(np.float64), (v[mask] - cy).astype(np.float64)
+    r2 = du * du + dv * dv
+    out = np.zeros(41)
+    out[0:4] = (len(m), du.sum(), dv.sum(), r2.sum())
+    out[4:7] = m.sum(0)
+    out[7:10] = (du[:, None] * m).sum(0)
+    out[10:13] = (dv[:, None] * m).sum(0)
+    out[13:16] = (r2[:, None] * m).sum(0)
+    mm = np.stack([m[:, 0] * m[:, 0], m[:, 0] * m[:, 1], m[:, 0] * m[:, 2], m[:, 1] * m[:, 1], m[:, 1] * m[:, 2],
+                   m[:, 2] * m[:, 2]], 1)
+    out[16:22] = mm.sum(0)
+    out[22:28] = (du[:, None] * mm).sum(0)
+    out[28:34] = (dv[:, None] * mm).sum(0)
+    out[34:40] = (r2[:, None] * mm).sum(0)
+    out[40] = len(m)
+    return out
+
+
+def _sym6(v):
+    return np.array([[v[0], v[1], v[2]], [v[1], v[3], v[4]], [v[2], v[4], v[5]]])
+
+
+def _nearest_rotation(e: np.ndarray) -> np.ndarray:
+    U, _, Vt = np.linalg.svd(e.reshape(3, 3))
+    R = U @ Vt
+    if np.linalg.det(R) < 0:
+        R = U @ np.diag([1.0, 1.0, -1.0]) @ Vt
+    return R.reshape(9)
+
+
+def _sqp_refine(r: np.ndarray, Omega: np.ndarray, max_iter: int = 15, tol: float = 1e-10) -> np.ndarray:
+    """Sequential quadratic programming on min r^T Omega r s.t. r in SO(3) (rows of R in r)."""
+    for _ in range(max_iter):
+        r1, r2, r3 = r[0:3], r[3:6], r[6:9]
+        g = np.array([r1 @ r1 - 1, r2 @ r2 - 1, r3 @ r3 - 1, r1 @ r2, r1 @ r3, r2 @ r3])
+        J = np.zeros((6, 9))
+        J[0, 0:3] = 2 * r1
+        J[1, 3:6] = 2 * r2
+        J[2, 6:9] = 2 * r3
+        J[3, 0:3], J[3, 3:6] = r2, r1
+        J[4, 0:3], J[4, 6:9] = r3, r1
+        J[5, 3:6], J[5, 6:9] = r3, r2
+        U, S, Vt = np.linalg.svd(J)
+        d_rs = Vt[:6].T @ ((U.T @ (-g)) / S)      # min-norm solution of J d = -g
+        N = Vt[6:].T                               # null space of J (9 x 3)
+        A = N.T @ Omega @ N
+        y = -np.linalg.solve(A, N.T @ Omega @ (r + d_rs))
+        d = d_rs + N @ y
+        r = r + d
+        if d @ d < tol:
+            break
+    return r
+
+
+def sqpnp_from_moments(mom: np.ndarray, f: float):
+    """SQPnP (cv2.SOLVEPNP_SQPNP) from the reduced moments for focal f.  Returns (R, t) world-to-camera or None."""
+    n = mom[0]
+    if n < 4 or not np.isfinite(f) or f <= 0:
+        return None
+    s1, s2 = 1.0 / f, 1.0 / (f * f)
+    SQ = np.array([[n, 0, -s1 * mom[1]], [0, n, -s1 * mom[2]], [-s1 * mom[1], -s1 * mom[2], s2 * mom[3]]])
+    Sm, Sxm, Sym, Srm = mom[4:7], s1 * mom[7:10], s1 * mom[10:13], s2 * mom[13:16]
+    z3 = np.zeros(3)
+    QA = np.stack([np.concatenate([Sm, z3, -Sxm]), np.concatenate([z3, Sm, -Sym]), np.concatenate([-Sxm, -Sym, Srm])])
+    Mm, Mx, My, Mr = _sym6(mom[16:22]), s1 * _sym6(mom[22:28]), s1 * _sym6(mom[28:34]), s2 * _sym6(mom[34:40])
+    Z = np.zeros((3, 3))
+    AQA = np.block([[Mm, Z, -Mx], [Z, Mm, -My], [-Mx, -My, Mr]])
+    try:
+        P = -np.linalg.solve(SQ, QA)
+    except np.linalg.LinAlgError:
+        return None
+    Omega = AQA + QA.T @ P
+    Omega = 0.5 * (Omega + Omega.T)
+    w, V = np.linalg.eigh(Omega)  # ascending
+    mean_pt = Sm / n
+    best = None
+
+    def consider(e):
+        nonlocal best
+        for sgn in (1.0, -1.0):
+            r = _sqp_refine(_nearest_rotation(sgn * np.sqrt(3.0) * e), Omega)
+            r = _nearest_rotation(r)
+            R = r.reshape(3, 3)
+            t = P @ r
+            if R[2] @ mean_pt + t[2] <= 0:  # cheirality
+                continue
+            err = float(r @ Omega @ r)
+            if best is None or err < best[0]:
+                best = (err, R, t)
+
+    consider(V[:, 0])
+    k = 1
+    while k < 9 and (best is None or best[0] > 3 * w[k]):
+        consider(V[:, k])
+        k += 1
+    if best is None:
+        return None
+    return best[1], best[2]
+
+
+def gpu_fast_pnp_frames(ops, pts: "torch.Tensor", conf: "torch.Tensor", H: int, W: int, first_focal_of, im_focals,
+                        im_poses, frame_ids, niter_PnP: int = 10, thr_px: float = 5.0):
+    """fast_pnp (init_im_poses.py:824-865) for the frames of one window with the reductions on the GPU:
+    for each frame and each tentative focal, SQPnP on all masked points -> consensus set (reprojection error
+    < 5 px, the RANSAC criterion) -> SQPnP re-fit on the consensus set; the focal with the most inliers wins.
+    Frames are processed in order because frame k's tentative focals derive from frame k-1's result."""
+    F = len(frame_ids)
+    HW = H * W
+    cx, cy = W / 2, H / 2
+    S = max(W, H)
+    mom_all = ops.pnp_moments(pts, conf, F, HW, W, cx, cy).cpu().numpy()[:, 0]  # focal-independent
+    for k, img in enumerate(frame_ids):
+        focal = first_focal_of(k, img)
+        if focal is None:
+            tentative = list(np.geomspace(S / 2, S * 3, 63))
+        else:
+            lo, hi = -0.03 * S + focal, 0.03 * S + focal
+            tentative = [focal] + ([float(x) for x in np.geomspace(lo, hi, 2)] if lo > 0 else [])
+        tentative = [float(f) for f in tentative if np.isfinite(f) and f > 0]
+        sols = [sqpnp_from_moments(mom_all[k], f) for f in tentative]
+        ok = [i for i, s in enumerate(sols) if s is not None]
+        if ok:
+            gate = np.zeros((1, len(ok), 13), dtype=np.float32)
+            for j, i in enumerate(ok):
+                R, t = sols[i]
+                gate[0, j, :12] = np.concatenate([R, t[:, None]], 1).reshape(12)
+                gate[0, j, 12] = tentative[i]
+            import torch
+            g = torch.from_numpy(gate).to(pts.device)
+            mom_in = ops.pnp_moments(pts[k:k + 1], conf[k:k + 1], 1, HW, W, cx, cy, gate=g, ncand=len(ok),
+                                     thr_px=thr_px).cpu().numpy()[0]
+            best = (0, None, None)
+            for j, i in enumerate(ok):
+                ninl = int(round(mom_in[j, 40]))
+                if ninl < 4 or ninl <= best[0]:
+                    continue
+                sol = sqpnp_from_moments(mom_in[j], tentative[i])
+                if sol is not None:
+                    best = (ninl, sol, tentative[i])
+            if best[0]:
+                R, t = best[1]
+                w2c = np.eye(4)
+                w2c[:3, :3], w2c[:3, 3] = R, t
+                im_focals[img], im_poses[img] = best[2], np.linalg.inv(w2c)
+        if im_poses[img] is None:
+            im_poses[img] = np.eye(4)
+
+
+def gpu_focal_per_group(ops, ref_pts: "torch.Tensor", ref_conf: "torch.Tensor", H: int, W: int):
+    """focal_per_group with the sums on the GPU: 1-D damped Newton on the z-shift from s = 0 (the reference runs
+    scipy's LM from the same start; both stop at the local minimiser of sum |f p - uv|^2)."""
+    import torch
+    G = ref_pts.shape[0]
+    HW = H * W
+    zoff = float(1.0 - ref_pts[..., 2].min())  # z - min(z over all reference frames) + 1
+    shift = torch.zeros(G, device=ref_pts.device)
+
+    def evaluate(s):
+        o = ops.shift_focal_sums(ref_pts, ref_conf, G, HW, W, H, s, zoff).cpu().numpy()
+        S1, S2, d1, d2, uv2 = o[:, 0], o[:, 1], o[:, 2], o[:, 3], o[:, 4]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            cost = uv2 - S1 * S1 / S2
+            grad = -(2 * S1 * d1 * S2 - S1 * S1 * d2) / (S2 * S2)
+        return cost, grad, S1 / S2, o[:, 5]
+
+    s = np.zeros(G)
+    cost, grad, foc, npts = evaluate(shift)
+    h = 1e-3
+    for _ in range(30):
+        # secant Newton on the 1-D gradient
+        shift.copy_(torch.from_numpy((s + h).astype(np.float32)))
+        _, grad_h, _, _ = evaluate(shift)
+        curv = (grad_h - grad) / h
+        step = np.where(curv > 0, -grad / np.where(curv > 0, curv, 1.0), -np.sign(grad) * 0.1)
+        step = np.clip(step, -0.5, 0.5)
+        s_new = s + step
+        shift.copy_(torch.from_numpy(s_new.astype(np.float32)))
+        cost_new, grad_new, foc_new, _ = evaluate(shift)
+        better = cost_new <= cost
+        s = np.where(better, s_new, s)
+        done = np.abs(np.where(better, cost - cost_new, 0.0)) <= 1e-3 * 1e-3 * np.maximum(cost, 1e-30)
+        cost, grad, foc = np.where(better, cost_new, cost), np.where(better, grad_new, grad), np.where(better, foc_new, foc)
+        if np.all(done | ~better):
+            break
+    if not np.all(np.isfinite(foc)) or np.any(npts < 1):
+        raise ValueError("shift/focal fit failed")
+    foc = torch.tensor(foc, dtype=torch.float32)
+    diag = (H ** 2 + W ** 2) ** 0.5
+    fx = 0.5 / torch.tan(torch.atan(W / diag / foc))
+    fy = 0.5 / torch.tan(torch.atan(H / diag / foc))
+    focal_group = ((fx * W) + (fy * H)) / 2
+    mean_f = focal_group[focal_group > 30].mean()
+    rel = torch.abs(focal_group - mean_f) / mean_f
+    focal_group[rel > 0.6] = mean_f
+    return focal_group.numpy().tolist()

@@ -335,6 +335,24 @@ def delta125(x, y, w, n_per_group: int, G: int, st, st_stride: int) -> torch.Ten
     return out
 
 
+def pnp_moments(pts: torch.Tensor, conf: torch.Tensor, F: int, HW: int, W: int, cx: float, cy: float,
+                gate: Optional[torch.Tensor] = None, ncand: int = 1, thr_px: float = 5.0) -> torch.Tensor:
+    """pts [F, HW, 3], conf [F, HW] fp32 contiguous; gate [F, ncand, 13] (w2c 3x4 row-major + focal) or None.
+    Returns [F, ncand, 41] fp64 moments."""
+    out = torch.empty((F, ncand, 41), device=pts.device, dtype=torch.float64)
+    check(lib().geo4d_pnp_moments(_vp(pts), _vp(conf), F, HW, W, C.c_float(cx), C.c_float(cy), _vp(gate), ncand,
+                                  C.c_float(thr_px), _vp(out), _s()), "geo4d_pnp_moments")
+    return out
+
+
+def shift_focal_sums(pts: torch.Tensor, conf: torch.Tensor, G: int, HW: int, W: int, H: int, shift: torch.Tensor,
+                     zoff: float) -> torch.Tensor:
+    out = torch.empty((G, 6), device=pts.device, dtype=torch.float64)
+    check(lib().geo4d_shift_focal_sums(_vp(pts), _vp(conf), G, HW, W, H, _vp(shift), C.c_float(zoff), _vp(out), _s()),
+          "geo4d_shift_focal_sums")
+    return out
+
+
 # --------------------------------------------------------------------------- launch accounting
 _replayed_kernels = 0
 

@@ -182,6 +182,15 @@ int geo4d_lad_step(const float* x, const float* y, int64_t n_per_group, int G, f
 int geo4d_delta125(const float* x, const float* y, const float* w, int64_t n_per_group, int G, const float* st,
                    int st_stride, double* out, g4_stream_t stream);
 
+/* Initialisation solvers of the alignment on the GPU (the reference runs them on the CPU through
+ * cv2.solvePnPRansac(SOLVEPNP_SQPNP) and scipy least_squares; init_im_poses.py:824-865,
+ * utils/geometry.py:162-270).  The kernels reduce the (focal-independent) SQPnP moments and the shift/focal
+ * sums; the 9x9 / 1-D solves stay on the host (geo4d_b200/init_solvers.py).  See csrc/align.cu for layouts. */
+int geo4d_pnp_moments(const float* pts, const float* conf, int F, int HW, int W, float cx, float cy,
+                      const float* gate, int C, float thr_px, double* out, g4_stream_t stream);
+int geo4d_shift_focal_sums(const float* pts, const float* conf, int G, int HW, int W, int H, const float* shift,
+                           float zoff, double* out, g4_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

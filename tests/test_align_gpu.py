@@ -107,3 +107,50 @@ def test_aligner_vs_oracle(cuda_device, graph):
     assert float(ang.max()) < 0.1
     assert abs(float(scene.get_focals()[0]) - r["focal"]) / r["focal"] < 1e-2
     assert abs(float(scene.s_depth[0]) - float(r["s_depth"][0])) < 2e-2
+
+
+def _pinhole_scene(H, W, f, c2w, seed=0, noise=0.002):
+    ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    depth = 2 + 1.5 * np.sin(xs / W * 3.1) * np.cos(ys / H * 2.3)
+    cam = np.stack([(xs - W / 2) / f * depth, (ys - H / 2) / f * depth, depth], -1)
+    pts = cam @ c2w[:3, :3].T + c2w[:3, 3]
+    return (pts + noise * np.random.RandomState(seed).randn(*pts.shape)).astype(np.float32)
+
+
+def test_gpu_pnp_and_focal_solvers_vs_cv2_scipy(cuda_device):
+    """GPU-reduced init solvers vs the library calls the reference makes (cv2.solvePnPRansac SQPNP, scipy LM)."""
+    from geo4d_b200 import init_solvers as isv, ops
+    H, W, f = 96, 128, 0.9 * 128
+    frames = []
+    for k in range(3):
+        a = 0.1 * k
+        c2w = np.eye(4)
+        c2w[:3, :3] = [[math.cos(a), 0, math.sin(a)], [0, 1, 0], [-math.sin(a), 0, math.cos(a)]]
+        c2w[:3, 3] = [0.1 * k, -0.05 * k, 0.02 * k]
+        frames.append((c2w, _pinhole_scene(H, W, f, c2w, seed=k)))
+    pts = torch.tensor(np.stack([p for _, p in frames])).reshape(3, H * W, 3).to(cuda_device)
+    conf = torch.ones(3, H * W, device=cuda_device)
+    conf[:, : 4 * W] = 0.0
+    # moments kernel vs numpy
+    mom = ops.pnp_moments(pts, conf, 3, H * W, W, W / 2, H / 2).cpu().numpy()[:, 0]
+    msk = (conf[0] > 0.5).reshape(H, W).cpu().numpy()
+    ref_mom = isv.moments_numpy(frames[0][1], msk, W / 2, H / 2)
+    assert np.allclose(mom[0], ref_mom, rtol=2e-5, atol=1e-3)
+    # per-frame PnP vs cv2 RANSAC
+    im_f, im_p = [None] * 3, [None] * 3
+    isv.gpu_fast_pnp_frames(ops, pts, conf, H, W, lambda k, img: f * 1.01 if k == 0 else im_f[img - 1], im_f, im_p,
+                            [0, 1, 2])
+    for k in range(3):
+        res = isv.fast_pnp(frames[k][1], f * 1.01 if k == 0 else im_f[k - 1], msk, 10)
+        assert res is not None and im_p[k] is not None
+        assert abs(im_f[k] - res[0]) < 1e-6
+        assert np.abs(im_p[k] - res[1]).max() < 2e-3
+        assert np.abs(im_p[k] - frames[k][0]).max() < 2e-2
+    # focal from the reference frame's point map vs scipy LM (camera-frame points of frame 0 of each "window")
+    ref_pts = torch.tensor(np.stack([_pinhole_scene(H, W, f, np.eye(4), seed=5), _pinhole_scene(H, W, 1.1 * f, np.eye(4), seed=6)]))
+    ref_conf = torch.ones(2, H, W)
+    host = isv.focal_per_group(ref_pts, ref_conf)
+    dev = isv.gpu_focal_per_group(ops, ref_pts.reshape(2, H * W, 3).to(cuda_device).contiguous(),
+                                  ref_conf.reshape(2, H * W).to(cuda_device).contiguous(), H, W)
+    for a, b in zip(host, dev):
+        assert abs(a - b) / a < 1e-2, (host, dev)
