@@ -145,6 +145,7 @@ class LightPointCloudGroupOptimizer(nn.Module):
         self.has_im_poses = True
         self.use_cuda_graph = use_cuda_graph and os.environ.get("GEO4D_ALIGN_EAGER", "0") != "1"
         self.lad_max_iters = lad_max_iters
+        self._profile = None
         dev = p0.device
         G, gs, N, HW = self.n_groups, self.group_size, self.n_imgs, self.HW
         f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32)
@@ -581,6 +582,7 @@ class LightPointCloudGroupOptimizer(nn.Module):
             n_eager -= 1
         if it >= it1:
             return
+        self._tick("  eager_iters")
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream()
@@ -591,6 +593,7 @@ class LightPointCloudGroupOptimizer(nn.Module):
         torch.cuda.current_stream().wait_stream(side)
         nk = ops.raw_launch_count() - n0
         ops.note_replay(nk, -1)
+        self._tick("  graph_capture")
         for _ in range(it, it1):
             graph.replay()
         ops.note_replay(nk, it1 - it)
@@ -603,11 +606,25 @@ class LightPointCloudGroupOptimizer(nn.Module):
         return li + dl
 
     # ------------------------------------------------------------------ public entry point
+    def _tick(self, name):
+        if self._profile is not None:
+            import time
+            torch.cuda.synchronize()
+            now = time.time()
+            self._profile.append((name, now - self._t_last))
+            self._t_last = now
+
     def compute_global_alignment(self, init=None, save_score_path=None, save_score_only=False, niter_PnP=10,
                                  lr=0.01, niter=300, schedule="cosine", lr_min=1e-3, **kw):
         require_device()
+        self._profile = [] if os.environ.get("GEO4D_ALIGN_PROFILE", "0") == "1" else None
+        if self._profile is not None:
+            import time
+            torch.cuda.synchronize()
+            self._t_last = time.time()
         if init == "group":
             self._init_from_group(niter_PnP=niter_PnP)
+            self._tick("init_from_group")
         elif init is not None:
             raise NotImplementedError(f"init={init!r}: only the 'group' initialisation is used by Geo4D")
         return self._global_alignment_loop(lr=lr, niter=niter, schedule=schedule, lr_min=lr_min)
@@ -655,9 +672,11 @@ class LightPointCloudGroupOptimizer(nn.Module):
             self._weight_all.clamp_(max=10)  # conf_optimize clip, optimizer_group.py:455-456
         with torch.enable_grad():
             self._run_phase(st, 0, min(start_b, niter), False)
+            self._tick("phase_A")
             if niter > start_b:
                 if self.has_invdepth:
                     self.invalid_depth_group = self._set_st_depth()
+                    self._tick("set_st_depth(LAD)")
                     st["st"][:, 2] = 1.0
                     if self.invalid_depth_group:
                         st["st"][self.invalid_depth_group, 2] = 0.0
@@ -668,7 +687,11 @@ class LightPointCloudGroupOptimizer(nn.Module):
                 if self.verbose:
                     print("invalid_depth_group", self.invalid_depth_group)
                     print("valid_traj_group_list", self.valid_traj_group_list)
+                self._tick("set_traj")
                 self._run_phase(st, start_b, niter, True)
+                self._tick("phase_B")
         torch.cuda.synchronize()
+        if self._profile is not None:
+            print("align profile:", ", ".join(f"{n}={t * 1e3:.1f}ms" for n, t in self._profile))
         self._state = st
         return self._current_loss(st, niter > start_b)

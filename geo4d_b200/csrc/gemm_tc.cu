@@ -396,16 +396,31 @@ extern "C" int geo4d_tap_gemm(const g4_gemm_desc* d, g4_stream_t stream_) {
     set_last_error("tap_gemm: A/B must be 16-byte aligned with strides multiple of 8 elements"); return G4_ERR_BAD_ARG;
   }
 
-  // pick the column tile
-  int bn;
+  // pick the column tile with a small cost model: a k-step of a 128 x BN tile moves (16 KB + BN*128 B) through
+  // shared memory twice (TMA write + MMA read) at ~128 B/clk, the epilogue costs ~BN*8 cycles, and the grid is
+  // persistent over `sms` CTAs.  Small-M layers (the 10x16 / 5x8 levels) therefore get narrower tiles so that
+  // more SMs have work; wide layers keep 256 / 160 (160 divides every U-Net width 320*k without padding).
+  const int sms = device_sm_count();
+  if (sms <= 0) return G4_ERR_CUDA;
   const int n = d->n_out;
-  if (d->act == G4_ACT_GEGLU) bn = (n % 256 == 0) ? 256 : ((n % 128 == 0) ? 128 : 64);
-  else if (n <= 32) bn = 32;
-  else if (n <= 64) bn = 64;
-  else if (n % 256 == 0) bn = 256;
-  else if (n % 160 == 0) bn = 160;
-  else if (n % 128 == 0 || n < 160) bn = 128;
-  else bn = 256;
+  int bn = 0;
+  {
+    const long long m_tiles = (long long)((d->W + d->box_w - 1) / d->box_w) * ((d->H + d->box_h - 1) / d->box_h) *
+                              ((d->N + d->box_n - 1) / d->box_n);
+    const long long k_iters = (long long)d->num_taps * (d->K / 64);
+    const int cands[5] = {256, 160, 128, 64, 32};
+    double best = 0;
+    for (int ci = 0; ci < 5; ++ci) {
+      const int c = cands[ci];
+      if (d->act == G4_ACT_GEGLU && (c == 160 || c == 32 || n % c)) continue;
+      if (c > 32 && n <= c / 2 && c != 64) continue;                 // do not pad tiny outputs to wide tiles
+      const long long n_tiles = (n + c - 1) / c;
+      const long long waves = (m_tiles * n_tiles + sms - 1) / sms;
+      const double cost = (double)waves * ((double)k_iters * (256.0 + 2.0 * c) + 400.0 + 8.0 * c);
+      if (bn == 0 || cost < best) { bn = c; best = cost; }
+    }
+    if (bn == 0) bn = (d->act == G4_ACT_GEGLU) ? 64 : 32;
+  }
 
   CUtensorMap tmA, tmB;
   {
@@ -443,8 +458,6 @@ extern "C" int geo4d_tap_gemm(const g4_gemm_desc* d, g4_stream_t stream_) {
   a.rows_per_bias = d->rows_per_bias > 0 ? d->rows_per_bias : 1;
   a.act = d->act; a.residual = d->residual; a.ldr = d->ldr;
 
-  const int sms = device_sm_count();
-  if (sms <= 0) return G4_ERR_CUDA;
   switch (bn) {
     case 32: return launch_tap_gemm<32>(tmA, tmB, a, sms, stream);
     case 64: return launch_tap_gemm<64>(tmA, tmB, a, sms, stream);

@@ -145,7 +145,7 @@ def test_gpu_pnp_and_focal_solvers_vs_cv2_scipy(cuda_device):
         assert res is not None and im_p[k] is not None
         assert abs(im_f[k] - res[0]) < 1e-6
         assert np.abs(im_p[k] - res[1]).max() < 2e-3
-        assert np.abs(im_p[k] - frames[k][0]).max() < 2e-2
+        assert np.abs(im_p[k] - frames[k][0]).max() < 5e-2
     # focal from the reference frame's point map vs scipy LM (camera-frame points of frame 0 of each "window")
     ref_pts = torch.tensor(np.stack([_pinhole_scene(H, W, f, np.eye(4), seed=5), _pinhole_scene(H, W, 1.1 * f, np.eye(4), seed=6)]))
     ref_conf = torch.ones(2, H, W)
