@@ -10,10 +10,11 @@ Same constructor arguments, `compute_global_alignment(init='group', niter, sched
   depth scale-shift -- is ONE fused kernel per iteration (geo4d_align_iter); the weighted Umeyama
   registrations, the LAD scale/shift fit (same Adam iteration as the reference, batched over windows and
   sync-free) and the delta<1.25 gate are reduction kernels (csrc/align.cu);
-* the O(N + G) small-parameter chain rule (quaternion / signed-log / log-scale parametrisations, the two
-  pose-graph terms) stays in torch autograd on tensors of a few hundred floats, driven by the matrix-form
-  gradients the kernel reduces, and the whole iteration is replayed from a CUDA graph (two graphs:
-  before / after `depth_traj_start_iter`);
+* the O(N + G) small-parameter part (chain rule to the quaternion / signed-log / log-scale parametrisations,
+  temporal-smoothing and trajectory-prior terms, Adam) is a second, single-CTA kernel
+  (geo4d_align_small_step) fed by the matrix-form gradients the dense kernel reduces; an iteration is two
+  kernels + a counter bump, replayed from a CUDA graph.  GEO4D_ALIGN_AUTOGRAD=1 switches that small part to
+  torch autograd + torch.optim.Adam (used by the tests to cross-check the hand-derived gradients);
 * the initialisation solvers the reference runs on the CPU -- the shift/focal least-squares fit (scipy LM) and
   the per-frame RANSAC-PnP (cv2, SQPnP) -- reduce their per-pixel sums on the GPU (geo4d_shift_focal_sums,
   geo4d_pnp_moments) and solve only 1-D / 9x9 problems on the host (init_solvers.py); set
@@ -441,7 +442,7 @@ class LightPointCloudGroupOptimizer(nn.Module):
         def fit(lr, iters):
             state = torch.zeros(G, 9, device=dev)
             state[:, 0] = s_init
-            acc = torch.zeros(G * 3, device=dev, dtype=torch.float64)
+            acc = torch.zeros(G * 4, device=dev, dtype=torch.float64)
             chunk = 250
             graph = None
             done_iters = 0
@@ -572,6 +573,64 @@ class LightPointCloudGroupOptimizer(nn.Module):
             st["opts"][1].step()
         ops.advance_counter(st["it"], 1)
 
+    def _iteration_fused(self, st: dict):
+        """dense kernel + small-parameter kernel; no torch ops, no host sync"""
+        N, G, HW = self.n_imgs, self.n_groups, self.HW
+        ops.check(ops.lib().geo4d_align_iter(
+            ops._vp(self.im_depthmaps), ops._vp(st["m"]), ops._vp(st["v"]), ops._vp(self._stacked_pred_all),
+            ops._vp(self._weight_all), ops._vp(self._stacked_depthmap_all if self.has_invdepth else None),
+            ops._vp(self._edge_ptr), ops._vp(self._edge_idx), ops._vp(st["poses"]), ops._vp(st["S"]),
+            ops._vp(st["scal"]), ops._vp(st["invf"]), ops._vp(st["it"]), ops._vp(st["st"]), ops._vp(st["gpose"]),
+            ops._vp(st["gS"]), ops._vp(st["gscal"]), ops._vp(st["gst"]), N, G, HW, self.W, self.group_size,
+            self.max_edges_per_image, ops._s()), "geo4d_align_iter")
+        import ctypes as C
+        ops.check(ops.lib().geo4d_align_small_step(
+            ops._vp(self.im_poses), ops._vp(self.im_focals), ops._vp(self.pw_poses), ops._vp(self.s_depth),
+            ops._vp(self.t_depth), ops._vp(self.traj_align_poses), ops._vp(st["adam_small"]), ops._vp(st["gpose"]),
+            ops._vp(st["gS"]), ops._vp(st["gscal"]), ops._vp(st["gst"]), ops._vp(st["traj16"]), ops._vp(st["e_img"]),
+            ops._vp(self._edge_ptr), ops._vp(self._edge_idx), ops._vp(st["valid_traj"]), ops._vp(st["scal"]),
+            ops._vp(st["it"]), ops._vp(st["poses"]), ops._vp(st["S"]), ops._vp(st["invf"]), ops._vp(st["st"]), N, G,
+            self.group_size, st["start_b"], C.c_float(self.temporal_smoothing_weight),
+            C.c_float(self.translation_weight), C.c_float(self.base_scale), C.c_float(self.focal_break), ops._s()),
+            "geo4d_align_small_step")
+        ops.advance_counter(st["it"], 1)
+
+    @torch.no_grad()
+    def _refresh_matrices(self, st):
+        """pose / sim(3) / focal matrices for the dense kernel from the current parameters"""
+        N, G = self.n_imgs, self.n_groups
+        st["poses"].copy_(self.get_im_poses()[:, :3, :].reshape(N, 12))
+        st["S"].copy_(self.get_pw_poses()[:, :3, :].reshape(G, 12))
+        st["invf"].copy_((-self.im_focals / self.focal_break).exp().reshape(1))
+        st["st"][:, 0].copy_(self.s_depth[:, 0])
+        st["st"][:, 1].copy_(self.t_depth[:, 0])
+
+    def _run_phase_fused(self, st, it0, it1):
+        if it1 <= it0:
+            return
+        self._refresh_matrices(st)
+        self._iteration_fused(st)  # first iteration eagerly (sets kernel attributes, validates arguments)
+        n_left = it1 - it0 - 1
+        if n_left <= 0:
+            return
+        if not self.use_cuda_graph:
+            for _ in range(n_left):
+                self._iteration_fused(st)
+            return
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        n0 = ops.raw_launch_count()
+        with torch.cuda.stream(side), torch.cuda.graph(graph, stream=side):
+            self._iteration_fused(st)
+        torch.cuda.current_stream().wait_stream(side)
+        nk = ops.raw_launch_count() - n0
+        ops.note_replay(nk, -1)
+        for _ in range(n_left):
+            graph.replay()
+        ops.note_replay(nk, n_left)
+
     def _run_phase(self, st, it0, it1, phase_b):
         """iterations [it0, it1): a few eager ones (they also serve as the graph warm-up), then replays."""
         it = it0
@@ -668,10 +727,24 @@ class LightPointCloudGroupOptimizer(nn.Module):
         }
         opt_a.param_groups[0]["lr"] = lr_a
         opt_b.param_groups[0]["lr"] = lr_b
+        fused = os.environ.get("GEO4D_ALIGN_AUTOGRAD", "0") != "1"
+        if fused:
+            f = ops.lib().geo4d_align_small_adam_floats
+            import ctypes as C
+            f.restype = C.c_size_t
+            st["adam_small"] = torch.zeros(int(f(N, G)), device=dev)
+            st["traj16"] = (self._stacked_traj_all.reshape(G * self.group_size, 16).contiguous() if self.has_traj
+                            else torch.eye(4, device=dev).reshape(1, 16).repeat(G * self.group_size, 1))
+            st["e_img"] = self._e_all.to(torch.int32).contiguous()
+            st["valid_traj"] = torch.zeros(G, device=dev)
+            st["start_b"] = int(start_b)
         with torch.no_grad():
             self._weight_all.clamp_(max=10)  # conf_optimize clip, optimizer_group.py:455-456
         with torch.enable_grad():
-            self._run_phase(st, 0, min(start_b, niter), False)
+            if fused:
+                self._run_phase_fused(st, 0, min(start_b, niter))
+            else:
+                self._run_phase(st, 0, min(start_b, niter), False)
             self._tick("phase_A")
             if niter > start_b:
                 if self.has_invdepth:
@@ -688,7 +761,12 @@ class LightPointCloudGroupOptimizer(nn.Module):
                     print("invalid_depth_group", self.invalid_depth_group)
                     print("valid_traj_group_list", self.valid_traj_group_list)
                 self._tick("set_traj")
-                self._run_phase(st, start_b, niter, True)
+                if fused:
+                    if self.has_traj and self.valid_traj_group_list:
+                        st["valid_traj"][self.valid_traj_group_list] = 1.0
+                    self._run_phase_fused(st, start_b, niter)
+                else:
+                    self._run_phase(st, start_b, niter, True)
                 self._tick("phase_B")
         torch.cuda.synchronize()
         if self._profile is not None:

@@ -175,7 +175,7 @@ int geo4d_align_iter(float* logd, float* adam_m, float* adam_v, const float* pre
                      int group_size, int max_edges_per_image, g4_stream_t stream);
 /* One Adam iteration of the LAD scale/shift fit min sum|s x + t - y| for G windows at once
  * (absolute_value_scaling2 depth_eval.py:112-145).  state[g] = {s, t, m_s, v_s, m_t, v_t, prev_loss,
- * step, done}; acc = 3*G doubles, zero before the first call. */
+ * step, done}; acc = 4*G doubles of scratch (3 sums + an arrival ticket per window), zero before the first call. */
 int geo4d_lad_step(const float* x, const float* y, int64_t n_per_group, int G, float* state, double* acc, float lr,
                    float tol, g4_stream_t stream);
 /* delta<1.25 accuracy of s*x+t vs y under (w>0.5 & x>0.05 & y>0) (depth_eval.py:296-317): out[g] = {ok, n}. */
@@ -190,6 +190,19 @@ int geo4d_pnp_moments(const float* pts, const float* conf, int F, int HW, int W,
                       const float* gate, int C, float thr_px, double* out, g4_stream_t stream);
 int geo4d_shift_focal_sums(const float* pts, const float* conf, int G, int HW, int W, int H, const float* shift,
                            float zoff, double* out, g4_stream_t stream);
+
+/* O(N + G) part of one alignment step: chain rule to the reference's pose / scale / focal parametrisations
+ * (base_opt_group.py:260-320, optimizer_group.py:193-198), temporal-smoothing and trajectory-prior terms
+ * (optimizer_group.py:492-542), torch.optim.Adam on every small parameter, and the refreshed matrices for the
+ * next geo4d_align_iter.  adam: geo4d_align_small_adam_floats(N, G) floats, zero-initialised. */
+size_t geo4d_align_small_adam_floats(int N, int G);
+int geo4d_align_small_step(float* im_poses, float* im_focal, float* pw_poses, float* s_depth, float* t_depth,
+                           float* ta_poses, float* adam, const double* gpose, const double* gS, const double* gscal,
+                           const double* gst, const float* traj, const int* e_img, const int* edge_ptr,
+                           const int* edge_idx, const float* valid_traj, const float* scal, const int* it,
+                           float* poses_out, float* S_out, float* invf_out, float* st_out, int N, int G,
+                           int group_size, int start_b, float temporal_smoothing_weight, float translation_weight,
+                           float base_scale, float focal_break, g4_stream_t stream);
 
 #ifdef __cplusplus
 }
