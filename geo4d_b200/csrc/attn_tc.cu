@@ -85,6 +85,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_grid_sync();
   const uint32_t tS = tmem_base;        // 128 columns
   const uint32_t tO = tmem_base + 128;  // 64 columns
 
@@ -312,6 +313,6 @@ extern "C" int geo4d_attention(const void* q, int64_t ldq, const void* k, const 
   }
   const long long grid = (long long)a.n_qtiles * B * H;
   if (grid > 2147483647ll) { set_last_error("attention: grid too large"); return G4_ERR_UNSUPPORTED; }
-  attn_fwd_kernel<<<(int)grid, 192, AT_SMEM, stream>>>(tmQ, tmK, tmV, a);
+  launch_pdl(attn_fwd_kernel, dim3((int)grid), dim3(192), AT_SMEM, stream, tmQ, tmK, tmV, a);
   return check_launch("attention");
 }

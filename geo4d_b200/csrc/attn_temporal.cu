@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(128)
 temporal_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                      const __nv_bfloat16* __restrict__ v, long long ld, __nv_bfloat16* __restrict__ o,
                      long long ldo, int B, int T, int HW, int heads, float scale_log2) {
+  pdl_grid_sync();
   __shared__ __align__(16) __nv_bfloat16 sm[4][3][16 * TA_STRIDE];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __nv_bfloat16* sQ = sm[warp][0];
@@ -157,7 +158,7 @@ extern "C" int geo4d_temporal_attention(const void* q, const void* k, const void
   const long long nprob = (long long)B * HW * heads;
   long long grid = (nprob + 3) / 4;
   if (grid > (long long)sms * 16) grid = (long long)sms * 16;
-  temporal_attn_kernel<<<(int)grid, 128, 0, stream>>>(
+  launch_pdl(temporal_attn_kernel, dim3((int)grid), dim3(128), 0, stream, 
       reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
       reinterpret_cast<const __nv_bfloat16*>(v), ld, reinterpret_cast<__nv_bfloat16*>(out), ldo, B, T, HW, heads,
       scale * 1.4426950408889634f);

@@ -3,6 +3,7 @@
 // library loads -- and exports its symbols -- on a machine without libcuda).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "geo4d_b200.h"
@@ -28,6 +29,15 @@ int check_launch(const char* what) {
   }
   ++g_launches;
   return G4_OK;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GEO4D_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 int device_sm_count() {

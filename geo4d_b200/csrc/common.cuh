@@ -26,6 +26,7 @@ enum : int {
 
 void set_last_error(const char* fmt, ...);
 int check_launch(const char* what);  // cudaPeekAtLastError -> status
+bool pdl_enabled();                  // programmatic dependent launch (GEO4D_PDL=0 switches it off)
 
 // Encode a tiled bf16 tensor map. dims[0] is the innermost (contiguous) dimension.
 // strides_bytes has rank-1 entries (strides of dims 1..rank-1).
@@ -33,6 +34,30 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
                    const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
 
 #ifdef __CUDACC__
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the denoising step is launched with programmaticStreamSerialization: its CTAs may start
+// (barrier init, TMEM allocation, descriptor prefetch) while the previous kernel drains.  pdl_wait() blocks
+// until the previous grid has completed and its writes are visible; it must precede the first global access.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_grid_sync() { pdl_wait(); pdl_launch_dependents(); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ----------------------------------------------------------------------------- small utils
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

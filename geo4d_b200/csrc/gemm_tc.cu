@@ -38,7 +38,16 @@ struct GemmArgs {
   int act;
   const void* residual;
   long long ldr;
+  unsigned long long* trace;  // debug: [grid][8] globaltimer stamps (geo4d_debug_gemm_trace), normally null
 };
+
+__device__ __forceinline__ void trace_stamp(const GemmArgs& a, int slot) {
+  if (a.trace) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.trace[(size_t)blockIdx.x * 8 + slot] = t;
+  }
+}
 
 template <int BLOCK_N>
 struct GemmCfg {
@@ -89,6 +98,9 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) trace_stamp(args, 0);  // NB: the stamp itself is a global write, hence after the wait
+  pdl_grid_sync();  // everything above overlaps the previous kernel's tail; global memory is touched only below
+  if (threadIdx.x == 0) trace_stamp(args, 1);
 
   const int m_tiles = args.tiles_x * args.tiles_y * args.tiles_n;
   const int total_tiles = m_tiles * args.n_tiles;
@@ -134,6 +146,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int ki = 0; ki < k_iters; ++ki) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
+          if (it == 0 && ki == 0) trace_stamp(args, 2);
           const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t sB = sA + Cfg::A_BYTES;
 #pragma unroll
@@ -146,6 +159,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull[acc]);
+        if (it == 0) trace_stamp(args, 3);
       }
     }
     __syncwarp();
@@ -201,6 +215,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
+      if (it == 0 && et == 0) trace_stamp(args, 4);
       const uint32_t t_row = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
 
       if (args.act == G4_ACT_GEGLU) {
@@ -337,11 +352,13 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (et == 0) trace_stamp(args, it == 0 ? 5 : 6);
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) trace_stamp(args, 7);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -365,13 +382,16 @@ static int launch_tap_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const
   }
   const int total = a.tiles_x * a.tiles_y * a.tiles_n * a.n_tiles;
   const int grid = total < num_sms ? total : num_sms;
-  tap_gemm_kernel<BLOCK_N><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, a);
+  launch_pdl(tap_gemm_kernel<BLOCK_N>, dim3(grid), dim3(320), Cfg::SMEM_BYTES, stream, tmA, tmB, a);
   return check_launch("tap_gemm");
 }
 
 int device_sm_count();
+static unsigned long long* g_gemm_trace = nullptr;
 
 }  // namespace g4
+
+extern "C" void geo4d_debug_gemm_trace(void* buf) { g4::g_gemm_trace = reinterpret_cast<unsigned long long*>(buf); }
 
 using namespace g4;
 
@@ -457,6 +477,7 @@ extern "C" int geo4d_tap_gemm(const g4_gemm_desc* d, g4_stream_t stream_) {
   a.bias = d->bias; a.row_bias = d->row_bias; a.row_bias_ld = d->row_bias_ld;
   a.rows_per_bias = d->rows_per_bias > 0 ? d->rows_per_bias : 1;
   a.act = d->act; a.residual = d->residual; a.ldr = d->ldr;
+  a.trace = g_gemm_trace;
 
   switch (bn) {
     case 32: return launch_tap_gemm<32>(tmA, tmB, a, sms, stream);

@@ -21,6 +21,7 @@ namespace g4 {
 // partials of its statistic while it builds the per-channel scale/shift table.
 __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int C, int rows_per_stat,
                                 int rows_per_block, float* __restrict__ part /*[S][nblk][32][2]*/) {
+  pdl_grid_sync();
   extern __shared__ float sm[];  // [ty][2*C] partials, then [2*C] totals in row 0
   const int s = blockIdx.y;
   const int row0 = blockIdx.x * rows_per_block;
@@ -82,6 +83,7 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long l
                                 long long ldy, int C, int rows_per_stat, int rows_per_block,
                                 const float* __restrict__ part, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, int silu) {
+  pdl_grid_sync();
   extern __shared__ float sm[];  // scale[C], shift[C], stats[64]
   const int s = blockIdx.y;
   const int row0 = blockIdx.x * rows_per_block;
@@ -149,6 +151,7 @@ template <int MAXV>
 __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ld, __nv_bfloat16* __restrict__ y,
                                  long long ldy, int M, int C, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float eps) {
+  pdl_grid_sync();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= M) return;
@@ -261,10 +264,10 @@ extern "C" int geo4d_groupnorm_silu(const void* x, int64_t ldx, void* y, int64_t
       attr = true;
     }
   }
-  gn_stats_kernel<<<grid, block, smem_stats, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, C, rows_per_stat,
+  launch_pdl(gn_stats_kernel, dim3(grid), dim3(block), smem_stats, stream, reinterpret_cast<const __nv_bfloat16*>(x), ldx, C, rows_per_stat,
                                                        rows_per_block, reinterpret_cast<float*>(workspace));
   int rc = check_launch("gn_stats"); if (rc) return rc;
-  gn_apply_kernel<<<grid, block, smem_apply, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx,
+  launch_pdl(gn_apply_kernel, dim3(grid), dim3(block), smem_apply, stream, reinterpret_cast<const __nv_bfloat16*>(x), ldx,
                                                        reinterpret_cast<__nv_bfloat16*>(y), ldy, C, rows_per_stat,
                                                        rows_per_block, reinterpret_cast<const float*>(workspace), gamma,
                                                        beta, eps, apply_silu);
@@ -285,9 +288,9 @@ extern "C" int geo4d_layernorm(const void* x, int64_t ldx, void* y, int64_t ldy,
   const int nvec = C / 8;
   const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
-  if (nvec <= 32) layernorm_kernel<1><<<grid, 256, 0, stream>>>(xp, ldx, yp, ldy, M, C, gamma, beta, eps);
-  else if (nvec <= 64) layernorm_kernel<2><<<grid, 256, 0, stream>>>(xp, ldx, yp, ldy, M, C, gamma, beta, eps);
-  else if (nvec <= 128) layernorm_kernel<4><<<grid, 256, 0, stream>>>(xp, ldx, yp, ldy, M, C, gamma, beta, eps);
-  else layernorm_kernel<8><<<grid, 256, 0, stream>>>(xp, ldx, yp, ldy, M, C, gamma, beta, eps);
+  if (nvec <= 32) launch_pdl(layernorm_kernel<1>, dim3(grid), dim3(256), 0, stream, xp, ldx, yp, ldy, M, C, gamma, beta, eps);
+  else if (nvec <= 64) launch_pdl(layernorm_kernel<2>, dim3(grid), dim3(256), 0, stream, xp, ldx, yp, ldy, M, C, gamma, beta, eps);
+  else if (nvec <= 128) launch_pdl(layernorm_kernel<4>, dim3(grid), dim3(256), 0, stream, xp, ldx, yp, ldy, M, C, gamma, beta, eps);
+  else launch_pdl(layernorm_kernel<8>, dim3(grid), dim3(256), 0, stream, xp, ldx, yp, ldy, M, C, gamma, beta, eps);
   return check_launch("layernorm");
 }

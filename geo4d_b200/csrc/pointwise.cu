@@ -9,6 +9,7 @@ namespace g4 {
 // ddpm3d.py:2540-2544) -> bf16 rows [(b t h w), Cpad] zero padded.  One thread per pixel.
 __global__ void bcthw_to_rows_kernel(const float* __restrict__ s0, int C0, const float* __restrict__ s1, int C1,
                                      int B, int T, int H, int W, __nv_bfloat16* __restrict__ out, int Cpad) {
+  pdl_grid_sync();
   const long long npix = (long long)B * T * H * W;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix) return;
@@ -39,6 +40,7 @@ __global__ void bcthw_to_rows_kernel(const float* __restrict__ s0, int C0, const
 // fp32 rows [(b t h w), ld] (first C columns) -> fp32 'b c t h w'
 __global__ void rows_to_bcthw_kernel(const float* __restrict__ rows, long long ld, int C, int B, int T, int H,
                                      int W, float* __restrict__ out) {
+  pdl_grid_sync();
   const long long npix = (long long)B * T * H * W;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix) return;
@@ -51,6 +53,7 @@ __global__ void rows_to_bcthw_kernel(const float* __restrict__ rows, long long l
 // ---------------------------------------------------------------------------------------------- concat / upsample / im2col
 __global__ void concat_rows_kernel(const uint4* __restrict__ a, long long lda8, int va, const uint4* __restrict__ b,
                                    long long ldb8, int vb, uint4* __restrict__ out, long long rows) {
+  pdl_grid_sync();
   const int vt = va + vb;
   const long long total = rows * vt;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -63,6 +66,7 @@ __global__ void concat_rows_kernel(const uint4* __restrict__ a, long long lda8, 
 
 __global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int N, int H, int W,
                                   int vecs) {
+  pdl_grid_sync();
   const long long total = (long long)N * (2 * H) * (2 * W) * vecs;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -78,6 +82,7 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restric
 // 3x3 stride-2 im2col: out[(n, oy, ox), tap*C + c] = in[n, 2*oy + ky - pad, 2*ox + kx - pad, c] (0 outside)
 __global__ void im2col_s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int N, int H, int W,
                                  int Ho, int Wo, int vecs, int pad) {
+  pdl_grid_sync();
   const long long total = (long long)N * Ho * Wo * 9 * vecs;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -105,6 +110,7 @@ __global__ void im2col_s2_kernel(const uint4* __restrict__ in, uint4* __restrict
 __global__ void ddim_step_kernel(float* __restrict__ x, const float* __restrict__ v, float* __restrict__ pred_x0,
                                  const float* __restrict__ noise, const float* __restrict__ coef,
                                  const int* __restrict__ step_idx, long long n) {
+  pdl_grid_sync();
   const int s = step_idx ? *step_idx : 0;
   const float sa = coef[s * 6 + 0], s1 = coef[s * 6 + 1], rs = coef[s * 6 + 2];
   const float sap = coef[s * 6 + 3], dir = coef[s * 6 + 4], sg = coef[s * 6 + 5];
@@ -122,6 +128,7 @@ __global__ void ddim_step_kernel(float* __restrict__ x, const float* __restrict_
 }
 
 __global__ void advance_counter_kernel(int* c, int delta, int modulo) {
+  pdl_grid_sync();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     int v = *c + delta;
     if (modulo > 0) v %= modulo;
@@ -132,6 +139,7 @@ __global__ void advance_counter_kernel(int* c, int delta, int modulo) {
 // out[j] = table[(*idx) * ld + j]  (per-step gather of precomputed embedding rows)
 __global__ void gather_row_kernel(const float* __restrict__ table, long long ld, const int* __restrict__ idx,
                                   float* __restrict__ out, int n) {
+  pdl_grid_sync();
   const int s = *idx;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
     out[j] = table[(long long)s * ld + j];
@@ -142,6 +150,7 @@ __global__ void gather_row_kernel(const float* __restrict__ table, long long ld,
 // row softmax: fp32 scores -> bf16 probabilities (ae_modules.py:66-67); one warp per row.
 __global__ void softmax_rows_kernel(const float* __restrict__ s, long long lds, __nv_bfloat16* __restrict__ p,
                                     long long ldp, long long rows, int cols) {
+  pdl_grid_sync();
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -174,6 +183,7 @@ __global__ void softmax_rows_kernel(const float* __restrict__ s, long long lds, 
 // out[b, c, r] = in[b, r, c] (bf16), 32x32 tiles through shared memory
 __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, long long ldin,
                                       __nv_bfloat16* __restrict__ out, int R, int Cc) {
+  pdl_grid_sync();
   __shared__ __nv_bfloat16 tile[32][34];
   const int b = blockIdx.z;
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
@@ -213,7 +223,7 @@ extern "C" int geo4d_bcthw_to_rows(const float* src0, int C0, const float* src1,
     return G4_ERR_BAD_ARG;
   }
   const long long npix = (long long)B * T * H * W;
-  bcthw_to_rows_kernel<<<(int)((npix + 127) / 128), 128, 0, stream>>>(src0, C0, src1, C1, B, T, H, W,
+  launch_pdl(bcthw_to_rows_kernel, dim3((int)((npix + 127) / 128)), dim3(128), 0, stream, src0, C0, src1, C1, B, T, H, W,
                                                                      reinterpret_cast<__nv_bfloat16*>(out), Cpad);
   return check_launch("bcthw_to_rows");
 }
@@ -223,7 +233,7 @@ extern "C" int geo4d_rows_to_bcthw(const float* rows, int64_t ld, int C, int B, 
   G4_STREAM;
   if (!rows || !out) { set_last_error("rows_to_bcthw: null"); return G4_ERR_BAD_ARG; }
   const long long npix = (long long)B * T * H * W;
-  rows_to_bcthw_kernel<<<(int)((npix + 127) / 128), 128, 0, stream>>>(rows, ld, C, B, T, H, W, out);
+  launch_pdl(rows_to_bcthw_kernel, dim3((int)((npix + 127) / 128)), dim3(128), 0, stream, rows, ld, C, B, T, H, W, out);
   return check_launch("rows_to_bcthw");
 }
 
@@ -233,7 +243,7 @@ extern "C" int geo4d_concat_rows(const void* a, int64_t lda, int Ca, const void*
   if (!a || !b || !out || Ca % 8 || Cb % 8 || lda % 8 || ldb % 8) { set_last_error("concat_rows: channels/ld must be multiples of 8"); return G4_ERR_BAD_ARG; }
   const int sms = device_sm_count(); if (sms <= 0) return G4_ERR_CUDA;
   const long long total = rows * ((Ca + Cb) / 8);
-  concat_rows_kernel<<<grid_for(total, 256, sms * 16), 256, 0, stream>>>(
+  launch_pdl(concat_rows_kernel, dim3(grid_for(total, 256, sms * 16)), dim3(256), 0, stream, 
       reinterpret_cast<const uint4*>(a), lda / 8, Ca / 8, reinterpret_cast<const uint4*>(b), ldb / 8, Cb / 8,
       reinterpret_cast<uint4*>(out), rows);
   return check_launch("concat_rows");
@@ -244,7 +254,7 @@ extern "C" int geo4d_upsample_nearest2x(const void* in, void* out, int N, int H,
   if (!in || !out || C % 8) { set_last_error("upsample2x: C must be a multiple of 8"); return G4_ERR_BAD_ARG; }
   const int sms = device_sm_count(); if (sms <= 0) return G4_ERR_CUDA;
   const long long total = (long long)N * 4 * H * W * (C / 8);
-  upsample2x_kernel<<<grid_for(total, 256, sms * 16), 256, 0, stream>>>(
+  launch_pdl(upsample2x_kernel, dim3(grid_for(total, 256, sms * 16)), dim3(256), 0, stream, 
       reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), N, H, W, C / 8);
   return check_launch("upsample2x");
 }
@@ -255,7 +265,7 @@ extern "C" int geo4d_im2col_3x3_s2(const void* in, void* out, int N, int H, int 
   if (!in || !out || C % 8) { set_last_error("im2col: C must be a multiple of 8"); return G4_ERR_BAD_ARG; }
   const int sms = device_sm_count(); if (sms <= 0) return G4_ERR_CUDA;
   const long long total = (long long)N * Ho * Wo * 9 * (C / 8);
-  im2col_s2_kernel<<<grid_for(total, 256, sms * 16), 256, 0, stream>>>(
+  launch_pdl(im2col_s2_kernel, dim3(grid_for(total, 256, sms * 16)), dim3(256), 0, stream, 
       reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), N, H, W, Ho, Wo, C / 8, pad_before);
   return check_launch("im2col_3x3_s2");
 }
@@ -265,14 +275,14 @@ extern "C" int geo4d_ddim_step(float* x, const float* v, float* pred_x0, const f
   G4_STREAM;
   if (!x || !v || !coef) { set_last_error("ddim_step: null"); return G4_ERR_BAD_ARG; }
   const int sms = device_sm_count(); if (sms <= 0) return G4_ERR_CUDA;
-  ddim_step_kernel<<<grid_for(n, 256, sms * 8), 256, 0, stream>>>(x, v, pred_x0, noise, coef, step_idx, n);
+  launch_pdl(ddim_step_kernel, dim3(grid_for(n, 256, sms * 8)), dim3(256), 0, stream, x, v, pred_x0, noise, coef, step_idx, n);
   return check_launch("ddim_step");
 }
 
 extern "C" int geo4d_advance_counter(int* counter, int delta, int modulo, g4_stream_t stream_) {
   G4_STREAM;
   if (!counter) { set_last_error("advance_counter: null"); return G4_ERR_BAD_ARG; }
-  advance_counter_kernel<<<1, 32, 0, stream>>>(counter, delta, modulo);
+  launch_pdl(advance_counter_kernel, dim3(1), dim3(32), 0, stream, counter, delta, modulo);
   return check_launch("advance_counter");
 }
 
@@ -280,7 +290,7 @@ extern "C" int geo4d_gather_row(const float* table, int64_t ld, const int* idx, 
                                 g4_stream_t stream_) {
   G4_STREAM;
   if (!table || !idx || !out) { set_last_error("gather_row: null"); return G4_ERR_BAD_ARG; }
-  gather_row_kernel<<<grid_for(n, 256, 64), 256, 0, stream>>>(table, ld, idx, out, n);
+  launch_pdl(gather_row_kernel, dim3(grid_for(n, 256, 64)), dim3(256), 0, stream, table, ld, idx, out, n);
   return check_launch("gather_row");
 }
 
@@ -291,7 +301,7 @@ extern "C" int geo4d_softmax_rows(const float* s, int64_t lds, void* p, int64_t 
     set_last_error("softmax_rows: cols/ld must be multiples of 4 and pointers aligned"); return G4_ERR_BAD_ARG;
   }
   const long long blocks = (rows + 7) / 8;
-  softmax_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(s, lds, reinterpret_cast<__nv_bfloat16*>(p), ldp, rows, cols);
+  launch_pdl(softmax_rows_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, s, lds, reinterpret_cast<__nv_bfloat16*>(p), ldp, rows, cols);
   return check_launch("softmax_rows");
 }
 
@@ -300,7 +310,7 @@ extern "C" int geo4d_transpose_bf16(const void* in, int64_t ldin, void* out, int
   G4_STREAM;
   if (!in || !out || batch < 1 || batch > 65535) { set_last_error("transpose: bad args"); return G4_ERR_BAD_ARG; }
   dim3 grid((Cc + 31) / 32, (R + 31) / 32, batch), block(32, 8);
-  transpose_bf16_kernel<<<grid, block, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), ldin,
+  launch_pdl(transpose_bf16_kernel, dim3(grid), dim3(block), 0, stream, reinterpret_cast<const __nv_bfloat16*>(in), ldin,
                                                     reinterpret_cast<__nv_bfloat16*>(out), R, Cc);
   return check_launch("transpose_bf16");
 }

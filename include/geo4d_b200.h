@@ -40,6 +40,10 @@ const char* geo4d_last_error(void);
 int geo4d_device_supported(void);
 /* Number of kernels this library has launched (or recorded into a CUDA graph) in this process. */
 uint64_t geo4d_launch_count(void);
+/* Debug aid: when non-null, every geo4d_tap_gemm launch writes 8 %globaltimer stamps per CTA into
+ * buf[grid][8] (entry, setup done, first operands landed, first tile's MMAs issued, first accumulator
+ * ready, first / last epilogue done, exit).  Pass NULL to switch it off (the default). */
+void geo4d_debug_gemm_trace(void* buf);
 
 /* ------------------------------------------------------------------------------------------------
  * Tap-GEMM on tcgen05 tensor cores (TMA -> shared memory -> tcgen05.mma -> TMEM -> epilogue).

@@ -157,32 +157,62 @@ def test_gpu_pnp_and_focal_solvers_vs_cv2_scipy(cuda_device):
         assert abs(a - b) / a < 1e-2, (host, dev)
 
 
-def test_fused_small_parameter_kernel_matches_autograd(cuda_device, monkeypatch):
-    """geo4d_align_small_step (hand-derived chain rule + pose terms + Adam) vs torch autograd + torch.optim.Adam
-    driven by the same dense kernel: the two trajectories must coincide up to fp32 rounding."""
+def _run_small(mode, monkeypatch, cuda_device, niter, start_b, graph=False):
     from oracle import align as oa
     from geo4d_b200.cloud_opt import LightPointCloudGroupOptimizer
     groups, preds, _ = oa.synthetic_scene(T=24, H=32, W=48, noise=0.003)
     views = [[{"idx": (i,)} for i in g] for g in groups]
-    outs = {}
-    for mode in ("1", "0"):
-        monkeypatch.setenv("GEO4D_ALIGN_AUTOGRAD", mode)
-        preds_d = [{k: v.to(cuda_device) for k, v in p.items()} for p in preds]
-        sc = LightPointCloudGroupOptimizer(views, preds_d, conf="id", conf_optimize=True, verbose=False,
-                                           shared_focal=True, num_total_iter=60, temporal_smoothing_weight=0.015,
-                                           translation_weight=1.0, depth_traj_start_iter=20, lad_max_iters=300,
-                                           use_cuda_graph=(mode == "0"))
-        with torch.enable_grad():
-            sc.compute_global_alignment(init="group", niter=60, schedule="linear", lr=0.03)
-        outs[mode] = (torch.stack(sc.get_depthmaps()).cpu(), sc.get_im_poses().detach().cpu(),
-                      float(sc.get_focals()[0]), sc.pw_poses.detach().cpu().clone(),
-                      sc.traj_align_poses.detach().cpu().clone(), sc.s_depth.detach().cpu().clone(),
-                      list(sc.valid_traj_group_list))
-    a, f = outs["1"], outs["0"]
-    assert a[6] == f[6] and len(a[6]) > 0  # the trajectory prior is active in this scene
-    assert float(((a[0] - f[0]).abs() / a[0]).mean()) < 2e-3
-    assert float((a[1] - f[1]).abs().max()) < 2e-3
-    assert abs(a[2] - f[2]) / a[2] < 2e-3
-    assert float((a[3] - f[3]).abs().max()) < 5e-3
-    assert float((a[4] - f[4]).abs().max()) < 5e-3
-    assert float((a[5] - f[5]).abs().max()) < 5e-3
+    monkeypatch.setenv("GEO4D_ALIGN_AUTOGRAD", mode)
+    preds_d = [{k: v.to(cuda_device) for k, v in p.items()} for p in preds]
+    sc = LightPointCloudGroupOptimizer(views, preds_d, conf="id", conf_optimize=True, verbose=False,
+                                       shared_focal=True, num_total_iter=niter, temporal_smoothing_weight=0.015,
+                                       translation_weight=1.0, depth_traj_start_iter=start_b, lad_max_iters=300,
+                                       use_cuda_graph=graph)
+    with torch.enable_grad():
+        loss = sc.compute_global_alignment(init="group", niter=niter, schedule="linear", lr=0.03)
+    return sc, loss
+
+
+SMALL = ["im_poses", "im_focals", "pw_poses", "s_depth", "t_depth", "traj_align_poses"]
+
+
+def test_fused_small_parameter_kernel_gradients_match_autograd(cuda_device, monkeypatch):
+    """geo4d_align_small_step's hand-derived chain rule (quaternion / signed-log translation / log-scale /
+    focal parameterisations, temporal-smoothing and trajectory-prior pose terms) vs torch autograd on the same
+    dense-kernel reductions.  With every term active from iteration 0 the first Adam moment is 0.1 * gradient,
+    so the kernel's gradient can be read back exactly and compared tensor by tensor."""
+    a, _ = _run_small("1", monkeypatch, cuda_device, niter=1, start_b=0)
+    f, _ = _run_small("0", monkeypatch, cuda_device, niter=1, start_b=0)
+    assert list(a.valid_traj_group_list) == list(f.valid_traj_group_list) and len(a.valid_traj_group_list) > 0
+    N, G = a.n_imgs, a.n_groups
+    m = f._state["adam_small"].double().cpu()
+    off = 0
+    def take(n):
+        nonlocal off
+        out = m[off:off + n]; off += 2 * n   # skip the second-moment block that follows each first-moment block
+        return out
+    got = {"im_poses": take(N * 7).view(N, 7) * 10, "im_focals": take(1) * 10, "pw_poses": take(G * 8).view(G, 8) * 10,
+           "s_depth": take(G) * 10, "t_depth": take(G) * 10, "traj_align_poses": take(G * 8).view(G, 8) * 10}
+    for name in SMALL:
+        ref = getattr(a, name).grad.double().cpu().reshape(got[name].shape)
+        scale = float(ref.abs().max())
+        assert scale > 0, name
+        err = float((got[name] - ref).abs().max()) / scale
+        assert err < 2e-3, (name, err, ref, got[name])
+
+
+def test_fused_small_parameter_kernel_trajectory(cuda_device, monkeypatch):
+    """Multi-step agreement.  Phase A (20 iterations, poses + focal + sim(3) only) must follow the autograd +
+    torch.optim.Adam trajectory to fp32 rounding.  Across the phase boundary the parameters are not comparable
+    one by one (the LAD fit leaves d loss / d(s, t) ~ 0, so the sign of Adam's first +-lr step is decided by
+    rounding); there the objective value and the geometry must agree instead."""
+    a, _ = _run_small("1", monkeypatch, cuda_device, niter=20, start_b=20)
+    f, _ = _run_small("0", monkeypatch, cuda_device, niter=20, start_b=20, graph=True)
+    for name in ("im_poses", "im_focals", "pw_poses", "im_depthmaps"):
+        d = float((getattr(a, name).detach() - getattr(f, name).detach()).abs().max())
+        assert d < 2e-4, (name, d)
+    a, la = _run_small("1", monkeypatch, cuda_device, niter=60, start_b=20)
+    f, lf = _run_small("0", monkeypatch, cuda_device, niter=60, start_b=20, graph=True)
+    assert abs(la - lf) / la < 0.1, (la, lf)
+    da, df = torch.stack(a.get_depthmaps()).cpu(), torch.stack(f.get_depthmaps()).cpu()
+    assert float(((da - df).abs() / da).mean()) < 2e-2
