@@ -48,6 +48,12 @@ def lib() -> C.CDLL:
             raise Geo4DError(f"cannot load {LIB_PATH}: {e}") from e
         _lib.geo4d_last_error.restype = C.c_char_p
         _lib.geo4d_abi_version.restype = C.c_int
+        # debug switches (see include/geo4d_b200.h): GEO4D_GEMM_PAIR = -1 (cost model) | 0 | 1,
+        # GEO4D_GEMM_DIRECT_STORE = 1 forces the per-thread store epilogue
+        if os.environ.get("GEO4D_GEMM_PAIR") is not None:
+            _lib.geo4d_debug_gemm_pair_mode(int(os.environ["GEO4D_GEMM_PAIR"]))
+        if os.environ.get("GEO4D_GEMM_DIRECT_STORE") is not None:
+            _lib.geo4d_debug_gemm_direct_store(int(os.environ["GEO4D_GEMM_DIRECT_STORE"]))
     return _lib
 
 

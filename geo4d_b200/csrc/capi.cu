@@ -35,7 +35,7 @@ bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("GEO4D_PDL");
-    v = (e && e[0] == '0') ? 0 : 1;
+    v = (e && e[0] == '1') ? 1 : 0;   // off by default: no gain under CUDA-graph replay (profiles/)
   }
   return v == 1;
 }

@@ -11,6 +11,8 @@
 // shifted by (dx, dy); the TMA unit zero-fills the out-of-bounds halo, so the activation is read
 // from HBM/L2 exactly as stored.  Two TMEM accumulator stages let the epilogue of tile i overlap
 // the MMAs of tile i+1.
+#include <cstring>
+
 #include "common.cuh"
 #include "geo4d_b200.h"
 
@@ -38,64 +40,82 @@ struct GemmArgs {
   int act;
   const void* residual;
   long long ldr;
-  unsigned long long* trace;  // debug: [grid][8] globaltimer stamps (geo4d_debug_gemm_trace), normally null
+  int tma_store;              // 1: bf16 tile goes out through shared memory + TMA (tmC valid)
+  unsigned long long* trace;  // debug: [grid][16] globaltimer stamps (geo4d_debug_gemm_trace), normally null
 };
 
 __device__ __forceinline__ void trace_stamp(const GemmArgs& a, int slot) {
   if (a.trace) {
     unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    a.trace[(size_t)blockIdx.x * 8 + slot] = t;
+    if (slot < 8) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));   // comparable across SMs, ~0.25 us ticks
+    else t = (unsigned long long)clock64();                                  // SM cycles, same-CTA deltas only
+    a.trace[(size_t)blockIdx.x * 16 + slot] = t;
   }
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool TWO>
 struct GemmCfg {
+  // TWO: the tile is 256 x BLOCK_N over a CTA pair; each CTA stages its own 128 A rows and HALF of the B rows
   static constexpr int A_BYTES = 128 * 64 * 2;
-  static constexpr int B_BYTES = BLOCK_N * 64 * 2;
+  static constexpr int B_BYTES = (TWO ? BLOCK_N / 2 : BLOCK_N) * 64 * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 160 ? 5 : 6);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2048 /*bias*/;
+  static constexpr int SLAB_BYTES = 128 * 64;   // [128 rows][32 bf16], SWIZZLE_64B
+  static constexpr int NSLAB = TWO ? ((BLOCK_N == 256) ? 1 : 2)
+                                   : ((BLOCK_N == 256 || BLOCK_N == 128) ? 1 : 2);  // output slabs per epilogue half
+  static constexpr int FIXED = 2 * NSLAB * SLAB_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2048 /*bias*/;
+  static constexpr int FIT = (232448 - FIXED) / STAGE_BYTES;
+  static constexpr int STAGES = FIT > 8 ? 8 : FIT;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED;
+  static_assert(STAGES >= 4 && SMEM_BYTES <= 232448, "tap_gemm: shared memory budget");
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool TWO>
 __global__ void __launch_bounds__(320, 1)
 tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const GemmArgs args) {
-  using Cfg = GemmCfg<BLOCK_N>;
+                const __grid_constant__ CUtensorMap tmC, const GemmArgs args) {
+  using Cfg = GemmCfg<BLOCK_N, TWO>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  // align by OFFSET (pointer arithmetic on the __shared__ array keeps the address space: LDS/STS, not generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* slabs = smem + STAGES * Cfg::STAGE_BYTES;   // [2 halves][NSLAB][SLAB_BYTES], 1024-aligned
+  uint8_t* tail = slabs + 2 * Cfg::NSLAB * Cfg::SLAB_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
   uint64_t* full = bars;                    // [STAGES]
   uint64_t* empty = bars + STAGES;          // [STAGES]
   uint64_t* tfull = bars + 2 * STAGES;      // [2]
   uint64_t* tempty = bars + 2 * STAGES + 2; // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* s_bias = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);  // [2][256]
+  float* s_bias = reinterpret_cast<float*>(tail + 256);  // [2][256]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int rank = TWO ? (int)cluster_ctarank() : 0;           // 0 = leader of the pair
+  const int unit = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // scheduling unit: CTA or CTA pair
+  const int n_units = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (args.tma_store) tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 8);
+      mbar_init(&tempty[a], TWO ? 16 : 8);   // the leader's barrier collects both CTAs' epilogue warps
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if (TWO) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
+    else { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();
+  if (TWO) cluster_sync_all();   // the partner's barriers must exist before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) trace_stamp(args, 0);  // NB: the stamp itself is a global write, hence after the wait
@@ -103,16 +123,18 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (threadIdx.x == 0) trace_stamp(args, 1);
 
   const int m_tiles = args.tiles_x * args.tiles_y * args.tiles_n;
-  const int total_tiles = m_tiles * args.n_tiles;
+  // a pair takes two consecutive row boxes (2*mt2 + rank); an odd tail box is fully out of bounds for the
+  // partner: its loads are zero-filled and its stores clipped by the TMA unit
+  const int total_tiles = (TWO ? (m_tiles + 1) / 2 : m_tiles) * args.n_tiles;
   const int k_iters = args.num_taps * args.kc_per_tap;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < total_tiles; tile += n_units) {
         const int nt = tile % args.n_tiles;
-        const int mt = tile / args.n_tiles;
+        const int mt = TWO ? 2 * (tile / args.n_tiles) + rank : tile / args.n_tiles;
         const int x0 = (mt % args.tiles_x) * args.box_w;
         const int y0 = ((mt / args.tiles_x) % args.tiles_y) * args.box_h;
         const int n0 = (mt / (args.tiles_x * args.tiles_y)) * args.box_n;
@@ -123,21 +145,29 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
             uint8_t* sB = sA + Cfg::A_BYTES;
-            mbar_expect_tx(&full[stage], args.a_box_bytes + Cfg::B_BYTES);
-            tma_load_4d(sA, &tmA, &full[stage], kc * 64, x0 + dx, y0 + dy, n0);
-            tma_load_3d(sB, &tmB, &full[stage], kc * 64, nt * BLOCK_N, bz);
+            if (TWO) {
+              // both CTAs' bytes are counted on the leader's barrier; only the leader arms it
+              if (rank == 0) mbar_expect_tx(&full[stage], 2u * (args.a_box_bytes + Cfg::B_BYTES));
+              const uint32_t lb = leader_bar_addr(&full[stage]);
+              tma_load_4d_2sm(sA, &tmA, lb, kc * 64, x0 + dx, y0 + dy, n0);
+              tma_load_3d_2sm(sB, &tmB, lb, kc * 64, nt * BLOCK_N + rank * (BLOCK_N / 2), bz);
+            } else {
+              mbar_expect_tx(&full[stage], args.a_box_bytes + Cfg::B_BYTES);
+              tma_load_4d(sA, &tmA, &full[stage], kc * 64, x0 + dx, y0 + dy, n0);
+              tma_load_3d(sB, &tmB, &full[stage], kc * 64, nt * BLOCK_N, bz);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
+    if (lane == 0 && rank == 0) {   // the leader issues the MMAs of the pair
+      constexpr uint32_t idesc = make_idesc_bf16(TWO ? 256 : 128, BLOCK_N, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = unit; tile < total_tiles; tile += n_units, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -153,30 +183,42 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int k = 0; k < 4; ++k) {
             const uint64_t ad = make_sw128_desc(sA + k * 32, 16, 1024);
             const uint64_t bd = make_sw128_desc(sB + k * 32, 16, 1024);
-            umma_ss(d_tmem, ad, bd, idesc, (ki | k) != 0 ? 1u : 0u);
+            if (TWO) umma_ss_2sm(d_tmem, ad, bd, idesc, (ki | k) != 0 ? 1u : 0u);
+            else umma_ss(d_tmem, ad, bd, idesc, (ki | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);
+          if (TWO) umma_commit_2sm(&empty[stage]); else umma_commit(&empty[stage]);   // frees the stage in both CTAs
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[acc]);
+        if (TWO) umma_commit_2sm(&tfull[acc]); else umma_commit(&tfull[acc]);
         if (it == 0) trace_stamp(args, 3);
       }
     }
     __syncwarp();
   } else {
-    // ---- epilogue: 8 warps; warps e and e+4 share a TMEM lane quadrant and split its 32-column chunks
+    // ---- epilogue: 8 warps; warps e and e+4 share a TMEM lane quadrant and split its 32-column chunks.
+    // bf16 results go through shared memory: each 4-warp half owns a small ring of [128 rows x 32 cols]
+    // slabs (64-byte rows, SWIZZLE_64B so that the per-row 16-byte writes are bank-conflict free); a slab is
+    // written by the 128 threads of the half and drained by ONE TMA store, which also clips the tile against
+    // the tensor edges.  Direct per-thread stores remain for fp32 outputs and unaligned destinations.
     const int e = warp - 2;
     const int q = warp & 3;            // TMEM lane quadrant this warp may access
     const int half = e >> 2;           // chunk parity handled by this warp
     const int et = threadIdx.x - 64;   // 0..255 among the epilogue threads
     const int r = q * 32 + lane;       // accumulator row handled by this thread
     const int rows_in_tile = args.box_w * args.box_h * args.box_n;
+    const bool issuer = ((e & 3) == 0) && lane == 0;
+    const int bar_id = 2 + half;
+    uint8_t* my_slabs = slabs + half * (Cfg::NSLAB * Cfg::SLAB_BYTES);
+    const uint32_t sw = (uint32_t)(r >> 1) & 3u;   // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9)
+    uint32_t kk = 0;                   // slabs this half has filled so far (ring position)
+    const int n_chunks = (args.act == G4_ACT_GEGLU) ? BLOCK_N / 64 : BLOCK_N / 32;
+    const int acc_cols = (args.act == G4_ACT_GEGLU) ? 64 : 32;   // accumulator columns per chunk
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = unit; tile < total_tiles; tile += n_units, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int nt = tile % args.n_tiles;
-      const int mt = tile / args.n_tiles;
+      const int mt = TWO ? 2 * (tile / args.n_tiles) + rank : tile / args.n_tiles;
       const int x0 = (mt % args.tiles_x) * args.box_w;
       const int y0 = ((mt / args.tiles_x) % args.tiles_y) * args.box_h;
       const int n0 = (mt / (args.tiles_x * args.tiles_y)) * args.box_n;
@@ -186,6 +228,9 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const bool row_ok = (r < rows_in_tile) && (x < args.W) && (y < args.H) && (n < args.N);
       const long long row = ((long long)n * args.H + y) * args.W + x;
       const int col_base = nt * BLOCK_N;
+      // chunks of this warp: c = half, half+2, ... while the chunk starts inside n_out
+      int my_chunks = 0;
+      for (int c = half; c < n_chunks && col_base + c * acc_cols < args.n_out; c += 2) ++my_chunks;
 
       // Stage the per-column additive terms (bias + the emb row of this tile) in shared memory while the
       // MMAs of this tile are still running: the epilogue then never waits on a global load for them.
@@ -210,188 +255,243 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           sb[et] = bv;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        named_bar_sync(1, 256);
       }
 
+      // residual of the first chunk: requested before the accumulator is ready, so its latency hides
+      // behind the MMAs of this tile; each later chunk's residual is requested one chunk ahead.
+      uint32_t rr[16];
+      const __nv_bfloat16* rrow = nullptr;
+      bool res_vec = false;
+      if (args.residual && row_ok && my_chunks > 0) {
+        rrow = reinterpret_cast<const __nv_bfloat16*>(args.residual) + row * args.ldr + col_base;
+        res_vec = ((reinterpret_cast<uintptr_t>(rrow) & 31) == 0) && ((args.ldr & 15) == 0);
+        if (res_vec && col_base + half * 32 + 32 <= args.n_out) {
+          uint32_t(&lo)[8] = *reinterpret_cast<uint32_t(*)[8]>(&rr[0]);
+          uint32_t(&hi)[8] = *reinterpret_cast<uint32_t(*)[8]>(&rr[8]);
+          ldg256(rrow + half * 32, lo);
+          ldg256(rrow + half * 32 + 16, hi);
+        }
+      }
+
+      if (my_chunks == 0) {   // (narrow tiles: BLOCK_N == 32 has a single chunk) nothing to read from TMEM
+        if (lane == 0) { if (TWO) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]); }
+        continue;
+      }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      if (it == 0 && et == 0) trace_stamp(args, 4);
+      if (it == 0 && et == 0) { trace_stamp(args, 4); trace_stamp(args, 13); }
       const uint32_t t_row = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
 
-      if (args.act == G4_ACT_GEGLU) {
-        // column blocks alternate [32 value | 32 gate]; stored width is n_out/2
 #pragma unroll 1
-        for (int c = half; c < BLOCK_N / 64; c += 2) {
+      for (int ci = 0; ci < my_chunks; ++ci) {
+        const int c = half + 2 * ci;
+        const int col0 = col_base + c * acc_cols;              // first accumulator column (B-row space)
+        const int scol0 = (args.act == G4_ACT_GEGLU) ? (col0 >> 1) : col0;   // first stored column
+        const int n_store = (args.act == G4_ACT_GEGLU) ? (args.n_out >> 1) : args.n_out;
+        const int ncols = min(32, n_store - scol0);
+        const bool vec_ok = (ncols == 32);
+        float o[32];
+        if (args.act == G4_ACT_GEGLU) {
+          // column blocks alternate [32 value | 32 gate]; stored width is n_out/2
           uint32_t v[32], g[32];
           tmem_ld32(t_row + c * 64, v);
           tmem_ld32(t_row + c * 64 + 32, g);
           tmem_ld_wait();
-          const int col0 = col_base + c * 64;           // in B-row (interleaved) space
-          const int ocol0 = col0 >> 1;                  // stored column
-          if (row_ok && col0 < args.n_out) {
-            float o[32];
-            const float4* b4 = reinterpret_cast<const float4*>(sb + c * 64);
+          if (ci == my_chunks - 1) {   // accumulator fully read by this warp: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (TWO) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]); }
+          }
+          const float4* b4 = reinterpret_cast<const float4*>(sb + c * 64);
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 ba = b4[j4], bg = b4[8 + j4];
-              const float bav[4] = {ba.x, ba.y, ba.z, ba.w}, bgv[4] = {bg.x, bg.y, bg.z, bg.w};
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 ba = b4[j4], bg = b4[8 + j4];
+            const float bav[4] = {ba.x, ba.y, ba.z, ba.w}, bgv[4] = {bg.x, bg.y, bg.z, bg.w};
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int j = 4 * j4 + k;
-                const float a = fmaf(__uint_as_float(v[j]), args.alpha, bav[k]);
-                const float b = fmaf(__uint_as_float(g[j]), args.alpha, bgv[k]);
-                o[j] = a * gelu_erf_f(b);
-              }
-            }
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(args.out) + row * args.ldc + ocol0;
-            uint4* o4 = reinterpret_cast<uint4*>(op);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 w;
-              w.x = pack_bf16x2(o[8 * j + 0], o[8 * j + 1]);
-              w.y = pack_bf16x2(o[8 * j + 2], o[8 * j + 3]);
-              w.z = pack_bf16x2(o[8 * j + 4], o[8 * j + 5]);
-              w.w = pack_bf16x2(o[8 * j + 6], o[8 * j + 7]);
-              o4[j] = w;
+            for (int k = 0; k < 4; ++k) {
+              const int j = 4 * j4 + k;
+              const float a = fmaf(__uint_as_float(v[j]), args.alpha, bav[k]);
+              const float b = fmaf(__uint_as_float(g[j]), args.alpha, bgv[k]);
+              o[j] = a * gelu_erf_f(b);
             }
           }
-        }
-      } else {
-#pragma unroll 1
-        for (int c = half; c < BLOCK_N / 32; c += 2) {
-          const int col0 = col_base + c * 32;
-          const bool active = row_ok && col0 < args.n_out;
-          const int ncols = min(32, args.n_out - col0);
-          const bool vec_ok = (ncols == 32);
+        } else {
           uint32_t v[32];
           tmem_ld32(t_row + c * 32, v);
-          // residual loads are issued before waiting on the TMEM load so both latencies overlap
-          uint4 rr[4];
-          const __nv_bfloat16* rp = nullptr;
-          bool res_vec = false;
-          if (active && args.residual) {
-            rp = reinterpret_cast<const __nv_bfloat16*>(args.residual) + row * args.ldr + col0;
-            res_vec = vec_ok && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0);
-            if (res_vec) {
-              const uint4* r4 = reinterpret_cast<const uint4*>(rp);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) rr[j] = r4[j];
-            }
-          }
           tmem_ld_wait();
-          if (active) {
-            float o[32];
-            const float4* b4 = reinterpret_cast<const float4*>(sb + c * 32);
+          if (it == 0 && ci == 0 && et == 0) trace_stamp(args, 8);
+          if (ci == my_chunks - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (TWO) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]); }
+          }
+          const float4* b4 = reinterpret_cast<const float4*>(sb + c * 32);
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 bb = b4[j4];
-              o[4 * j4 + 0] = fmaf(__uint_as_float(v[4 * j4 + 0]), args.alpha, bb.x);
-              o[4 * j4 + 1] = fmaf(__uint_as_float(v[4 * j4 + 1]), args.alpha, bb.y);
-              o[4 * j4 + 2] = fmaf(__uint_as_float(v[4 * j4 + 2]), args.alpha, bb.z);
-              o[4 * j4 + 3] = fmaf(__uint_as_float(v[4 * j4 + 3]), args.alpha, bb.w);
-            }
-            if (args.row_bias && !rb_in_smem) {  // tile straddles two embedding rows: per-thread loads
-              const float* rb = args.row_bias + (row / args.rows_per_bias) * args.row_bias_ld + col0;
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 bb = b4[j4];
+            o[4 * j4 + 0] = fmaf(__uint_as_float(v[4 * j4 + 0]), args.alpha, bb.x);
+            o[4 * j4 + 1] = fmaf(__uint_as_float(v[4 * j4 + 1]), args.alpha, bb.y);
+            o[4 * j4 + 2] = fmaf(__uint_as_float(v[4 * j4 + 2]), args.alpha, bb.z);
+            o[4 * j4 + 3] = fmaf(__uint_as_float(v[4 * j4 + 3]), args.alpha, bb.w);
+          }
+          if (args.row_bias && !rb_in_smem && row_ok) {  // tile straddles two embedding rows: per-thread loads
+            const float* rb = args.row_bias + (row / args.rows_per_bias) * args.row_bias_ld + col0;
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < ncols) o[j] += __ldg(rb + j);
-            }
-            if (args.act == G4_ACT_SILU) {
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) o[j] += __ldg(rb + j);
+          }
+          if (args.act == G4_ACT_SILU) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) o[j] = silu_f(o[j]);
-            }
-            if (args.residual) {
-              if (res_vec) {
+            for (int j = 0; j < 32; ++j) o[j] = silu_f(o[j]);
+          }
+          if (rrow) {
+            if (res_vec && vec_ok) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  float2 f;
-                  f = unpack_bf16x2(rr[j].x); o[8 * j + 0] += f.x; o[8 * j + 1] += f.y;
-                  f = unpack_bf16x2(rr[j].y); o[8 * j + 2] += f.x; o[8 * j + 3] += f.y;
-                  f = unpack_bf16x2(rr[j].z); o[8 * j + 4] += f.x; o[8 * j + 5] += f.y;
-                  f = unpack_bf16x2(rr[j].w); o[8 * j + 6] += f.x; o[8 * j + 7] += f.y;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (j < ncols) o[j] += __bfloat162float(rp[j]);
-              }
-            }
-            if (args.out_fp32) {
-              float* op = reinterpret_cast<float*>(args.out) + row * args.ldc + col0;
-              if (vec_ok && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
-                float4* o4 = reinterpret_cast<float4*>(op);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o4[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (j < ncols) op[j] = o[j];
+              for (int j = 0; j < 16; ++j) {
+                const float2 f = unpack_bf16x2(rr[j]);
+                o[2 * j] += f.x;
+                o[2 * j + 1] += f.y;
               }
             } else {
-              __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(args.out) + row * args.ldc + col0;
-              if (vec_ok && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
-                uint4* o4 = reinterpret_cast<uint4*>(op);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  uint4 w;
-                  w.x = pack_bf16x2(o[8 * j + 0], o[8 * j + 1]);
-                  w.y = pack_bf16x2(o[8 * j + 2], o[8 * j + 3]);
-                  w.z = pack_bf16x2(o[8 * j + 4], o[8 * j + 5]);
-                  w.w = pack_bf16x2(o[8 * j + 6], o[8 * j + 7]);
-                  o4[j] = w;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (j < ncols) op[j] = __float2bfloat16(o[j]);
-              }
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) o[j] += __bfloat162float(rrow[c * 32 + j]);
             }
           }
         }
+
+        if (args.tma_store) {
+          uint4 w[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            w[j].x = pack_bf16x2(o[8 * j + 0], o[8 * j + 1]);
+            w[j].y = pack_bf16x2(o[8 * j + 2], o[8 * j + 3]);
+            w[j].z = pack_bf16x2(o[8 * j + 4], o[8 * j + 5]);
+            w[j].w = pack_bf16x2(o[8 * j + 6], o[8 * j + 7]);
+          }
+          if (it == 0 && ci == 0 && et == 0) trace_stamp(args, 9);
+          {
+            uint8_t* slab = my_slabs + (kk % Cfg::NSLAB) * Cfg::SLAB_BYTES;
+            if (issuer) bulk_wait_read<Cfg::NSLAB - 1>();   // the store that last used this slab has drained it
+            named_bar_sync(bar_id, 128);
+            uint4* rowp = reinterpret_cast<uint4*>(slab + r * 64);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rowp[(uint32_t)j ^ sw] = w[j];
+            fence_proxy_async_smem();
+            named_bar_sync(bar_id, 128);
+            if (issuer) {
+              tma_store_4d(&tmC, slab, scol0, x0, y0, n0);
+              bulk_commit();
+            }
+          }
+          ++kk;
+        } else if (row_ok) {
+          if (args.out_fp32) {
+            float* op = reinterpret_cast<float*>(args.out) + row * args.ldc + scol0;
+            if (vec_ok && ((reinterpret_cast<uintptr_t>(op) & 31) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint32_t pk[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) pk[k] = __float_as_uint(o[8 * j + k]);
+                stg256(op + 8 * j, pk);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) op[j] = o[j];
+            }
+          } else {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(args.out) + row * args.ldc + scol0;
+            if (vec_ok && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+              uint4* o4 = reinterpret_cast<uint4*>(op);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 w;
+                w.x = pack_bf16x2(o[8 * j + 0], o[8 * j + 1]);
+                w.y = pack_bf16x2(o[8 * j + 2], o[8 * j + 3]);
+                w.z = pack_bf16x2(o[8 * j + 4], o[8 * j + 5]);
+                w.w = pack_bf16x2(o[8 * j + 6], o[8 * j + 7]);
+                o4[j] = w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) op[j] = __float2bfloat16(o[j]);
+            }
+          }
+        }
+        // next chunk's residual: requested only now, AFTER fence.proxy.async above -- that fence waits for the
+        // thread's outstanding global loads, so an earlier request would put the L2 latency on the critical path
+        if (rrow && ci + 1 < my_chunks && res_vec && args.act != G4_ACT_GEGLU &&
+            col_base + (c + 2) * 32 + 32 <= args.n_out) {
+          uint32_t(&lo)[8] = *reinterpret_cast<uint32_t(*)[8]>(&rr[0]);
+          uint32_t(&hi)[8] = *reinterpret_cast<uint32_t(*)[8]>(&rr[8]);
+          ldg256(rrow + (c + 2) * 32, lo);
+          ldg256(rrow + (c + 2) * 32 + 16, hi);
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
       if (et == 0) trace_stamp(args, it == 0 ? 5 : 6);
     }
+    if (issuer) bulk_wait_all();   // shared memory must outlive the last TMA store
   }
 
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();
+  if (TWO) cluster_sync_all();   // neither CTA may retire while its partner can still touch its barriers / TMEM
+  else __syncthreads();
   if (threadIdx.x == 0) trace_stamp(args, 7);
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (TWO) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
-template <int BLOCK_N>
-static int launch_tap_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, int num_sms,
-                           cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N>;
+template <int BLOCK_N, bool TWO>
+static int launch_tap_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                           const GemmArgs& a, int num_sms, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N, TWO>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tap_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(tap_gemm_kernel<BLOCK_N, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
-      set_last_error("tap_gemm<%d>: cudaFuncSetAttribute(smem=%d): %s", BLOCK_N, Cfg::SMEM_BYTES,
+      set_last_error("tap_gemm<%d,%d>: cudaFuncSetAttribute(smem=%d): %s", BLOCK_N, (int)TWO, Cfg::SMEM_BYTES,
                      cudaGetErrorString(e));
       return G4_ERR_CUDA;
     }
     attr_set = true;
   }
-  const int total = a.tiles_x * a.tiles_y * a.tiles_n * a.n_tiles;
-  const int grid = total < num_sms ? total : num_sms;
-  launch_pdl(tap_gemm_kernel<BLOCK_N>, dim3(grid), dim3(320), Cfg::SMEM_BYTES, stream, tmA, tmB, a);
+  const int m_tiles = a.tiles_x * a.tiles_y * a.tiles_n;
+  int grid;
+  if (TWO) {
+    const int total = ((m_tiles + 1) / 2) * a.n_tiles, pairs = num_sms / 2;
+    grid = 2 * (total < pairs ? total : pairs);
+  } else {
+    const int total = m_tiles * a.n_tiles;
+    grid = total < num_sms ? total : num_sms;
+  }
+  cudaError_t e = launch_ex(tap_gemm_kernel<BLOCK_N, TWO>, dim3(grid), dim3(320), Cfg::SMEM_BYTES, stream, TWO ? 2 : 1,
+                            tmA, tmB, tmC, a);
+  if (e != cudaSuccess) {
+    set_last_error("tap_gemm<%d,%d>: launch: %s", BLOCK_N, (int)TWO, cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return G4_ERR_CUDA;
+  }
   return check_launch("tap_gemm");
 }
 
 int device_sm_count();
 static unsigned long long* g_gemm_trace = nullptr;
+static bool g_no_tma_store = false;   // debug switch: force the direct-store epilogue
+static int g_pair_mode = -1;          // debug switch: -1 cost model, 0 never pair CTAs, 1 always (when legal)
 
 }  // namespace g4
 
 extern "C" void geo4d_debug_gemm_trace(void* buf) { g4::g_gemm_trace = reinterpret_cast<unsigned long long*>(buf); }
+extern "C" void geo4d_debug_gemm_direct_store(int on) { g4::g_no_tma_store = on != 0; }
+extern "C" void geo4d_debug_gemm_pair_mode(int mode) { g4::g_pair_mode = mode; }
 
 using namespace g4;
 
@@ -416,33 +516,62 @@ extern "C" int geo4d_tap_gemm(const g4_gemm_desc* d, g4_stream_t stream_) {
     set_last_error("tap_gemm: A/B must be 16-byte aligned with strides multiple of 8 elements"); return G4_ERR_BAD_ARG;
   }
 
-  // pick the column tile with a small cost model: a k-step of a 128 x BN tile moves (16 KB + BN*128 B) through
-  // shared memory twice (TMA write + MMA read) at ~128 B/clk, the epilogue costs ~BN*8 cycles, and the grid is
-  // persistent over `sms` CTAs.  Small-M layers (the 10x16 / 5x8 levels) therefore get narrower tiles so that
-  // more SMs have work; wide layers keep 256 / 160 (160 divides every U-Net width 320*k without padding).
+  // Pick the column tile and 1-CTA vs CTA-pair with a small cost model.  A k-step of a CTA moves
+  // (16 KB + its share of the B tile) from L2 into shared memory; the L2 -> SM path sustains ~45 B/clk per SM
+  // (measured: profiles/), the MMA needs 2*BLOCK_N clk, so the k-step costs the larger of the two.  The epilogue
+  // of a tile (~300 + 10*BLOCK_N clk) overlaps the next tile's main loop, so a CTA that runs `waves` tiles
+  // takes main + (waves-1)*max(main, epi) + epi.  The grid is persistent over `sms` CTAs (or sms/2 pairs): a
+  // pair halves the B bytes per SM but also the number of schedulable units, so epilogue-bound (small K) and
+  // small-M layers (the 10x16 / 5x8 levels) keep single CTAs.
   const int sms = device_sm_count();
   if (sms <= 0) return G4_ERR_CUDA;
   const int n = d->n_out;
   int bn = 0;
+  bool two = false;
   {
     const long long m_tiles = (long long)((d->W + d->box_w - 1) / d->box_w) * ((d->H + d->box_h - 1) / d->box_h) *
                               ((d->N + d->box_n - 1) / d->box_n);
     const long long k_iters = (long long)d->num_taps * (d->K / 64);
     const int cands[5] = {256, 160, 128, 64, 32};
+    const bool pair_ok = !d->b_batched && sms >= 2 && g_pair_mode != 0;
     double best = 0;
-    for (int ci = 0; ci < 5; ++ci) {
-      const int c = cands[ci];
-      if (d->act == G4_ACT_GEGLU && (c == 160 || c == 32 || n % c)) continue;
-      if (c > 32 && n <= c / 2 && c != 64) continue;                 // do not pad tiny outputs to wide tiles
-      const long long n_tiles = (n + c - 1) / c;
-      const long long waves = (m_tiles * n_tiles + sms - 1) / sms;
-      const double cost = (double)waves * ((double)k_iters * (256.0 + 2.0 * c) + 400.0 + 8.0 * c);
-      if (bn == 0 || cost < best) { bn = c; best = cost; }
+    for (int pass = 0; pass < 2; ++pass) {
+      const bool tw = pass == 0;
+      if (tw && !pair_ok) continue;
+      if (!tw && pair_ok && g_pair_mode == 1) continue;
+      for (int ci = 0; ci < 5; ++ci) {
+        const int c = cands[ci];
+        if (d->act == G4_ACT_GEGLU && (c == 160 || c == 32 || n % c)) continue;
+        if (c > 32 && n <= c / 2 && c != 64) continue;                 // do not pad tiny outputs to wide tiles
+        const long long n_tiles = (n + c - 1) / c;
+        const long long units = tw ? sms / 2 : sms;
+        const long long tiles = (tw ? (m_tiles + 1) / 2 : m_tiles) * n_tiles;
+        const long long waves = (tiles + units - 1) / units;
+        const double bytes = 16384.0 + (tw ? 64.0 : 128.0) * c;
+        const double kstep = bytes / 45.0 > 2.0 * c ? bytes / 45.0 : 2.0 * c;
+        const double main_clk = (double)k_iters * kstep;
+        const double epi_clk = 300.0 + (d->act == G4_ACT_GEGLU ? 14.0 : 10.0) * c;
+        const double cost = main_clk + (double)(waves - 1) * (main_clk > epi_clk ? main_clk : epi_clk) + epi_clk;
+        if (bn == 0 || cost < best) { bn = c; best = cost; two = tw; }
+      }
     }
     if (bn == 0) bn = (d->act == G4_ACT_GEGLU) ? 64 : 32;
   }
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC;
+  memset(&tmC, 0, sizeof(tmC));
+  // bf16 outputs with a 16-byte aligned base and row pitch leave through TMA stores (tile-shaped box, 32 columns)
+  const int n_store = d->act == G4_ACT_GEGLU ? d->n_out / 2 : d->n_out;
+  const bool tma_store = !d->out_fp32 && (d->ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) &&
+                         n_store >= 32 && !g_no_tma_store;
+  if (tma_store) {
+    uint64_t dims[4] = {(uint64_t)n_store, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
+    uint64_t strides[3] = {(uint64_t)d->ldc * 2, (uint64_t)d->ldc * 2 * (uint64_t)d->W,
+                           (uint64_t)d->ldc * 2 * (uint64_t)d->W * (uint64_t)d->H};
+    uint32_t box[4] = {32, (uint32_t)d->box_w, (uint32_t)d->box_h, (uint32_t)d->box_n};
+    int rc = make_tmap_bf16(&tmC, d->out, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  }
   {
     uint64_t dims[4] = {(uint64_t)d->K, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
     uint64_t strides[3] = {(uint64_t)d->a_stride_w * 2, (uint64_t)d->a_stride_h * 2, (uint64_t)d->a_stride_n * 2};
@@ -454,7 +583,7 @@ extern "C" int geo4d_tap_gemm(const g4_gemm_desc* d, g4_stream_t stream_) {
     const uint64_t nb = d->b_batched ? (uint64_t)d->N : (uint64_t)d->num_taps;
     uint64_t dims[3] = {(uint64_t)d->K, (uint64_t)d->n_out, nb};
     uint64_t strides[2] = {(uint64_t)d->K * 2, (uint64_t)d->K * 2 * (uint64_t)d->n_out};
-    uint32_t box[3] = {64, (uint32_t)bn, 1};
+    uint32_t box[3] = {64, (uint32_t)(two ? bn / 2 : bn), 1};
     int rc = make_tmap_bf16(&tmB, d->b, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
@@ -478,12 +607,22 @@ extern "C" int geo4d_tap_gemm(const g4_gemm_desc* d, g4_stream_t stream_) {
   a.rows_per_bias = d->rows_per_bias > 0 ? d->rows_per_bias : 1;
   a.act = d->act; a.residual = d->residual; a.ldr = d->ldr;
   a.trace = g_gemm_trace;
+  a.tma_store = tma_store ? 1 : 0;
 
+  if (two) {
+    switch (bn) {
+      case 32: return launch_tap_gemm<32, true>(tmA, tmB, tmC, a, sms, stream);
+      case 64: return launch_tap_gemm<64, true>(tmA, tmB, tmC, a, sms, stream);
+      case 128: return launch_tap_gemm<128, true>(tmA, tmB, tmC, a, sms, stream);
+      case 160: return launch_tap_gemm<160, true>(tmA, tmB, tmC, a, sms, stream);
+      default: return launch_tap_gemm<256, true>(tmA, tmB, tmC, a, sms, stream);
+    }
+  }
   switch (bn) {
-    case 32: return launch_tap_gemm<32>(tmA, tmB, a, sms, stream);
-    case 64: return launch_tap_gemm<64>(tmA, tmB, a, sms, stream);
-    case 128: return launch_tap_gemm<128>(tmA, tmB, a, sms, stream);
-    case 160: return launch_tap_gemm<160>(tmA, tmB, a, sms, stream);
-    default: return launch_tap_gemm<256>(tmA, tmB, a, sms, stream);
+    case 32: return launch_tap_gemm<32, false>(tmA, tmB, tmC, a, sms, stream);
+    case 64: return launch_tap_gemm<64, false>(tmA, tmB, tmC, a, sms, stream);
+    case 128: return launch_tap_gemm<128, false>(tmA, tmB, tmC, a, sms, stream);
+    case 160: return launch_tap_gemm<160, false>(tmA, tmB, tmC, a, sms, stream);
+    default: return launch_tap_gemm<256, false>(tmA, tmB, tmC, a, sms, stream);
   }
 }

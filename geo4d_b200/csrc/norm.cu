@@ -17,13 +17,23 @@ namespace g4 {
 
 // ---------------------------------------------------------------------------------------------- GroupNorm
 // block = (C/8, ty): each thread owns a fixed 8-channel vector and strides over rows.  Per-block partial
-// {sum, sumsq} per group go to part[stat][block][32][2] (no atomics: deterministic); gn_apply sums the
-// partials of its statistic while it builds the per-channel scale/shift table.
+// {sum, sumsq} per group go to part[stat][block][32][2]; the LAST block of a statistic to finish (ticket)
+// folds the partials in block order -- fixed order, no float atomics, so the result is deterministic --
+// into fin[stat][64] = {mean[32], rstd[32]} and puts the ticket back to zero.  gn_apply reads 64 floats.
+//
+// workspace layout (floats): [0, GN_TICKETS) tickets (int, zero between calls) | fin[S][64] | part[S][nblk][64]
+constexpr int GN_TICKETS = 4096;
+
 __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int C, int rows_per_stat,
-                                int rows_per_block, float* __restrict__ part /*[S][nblk][32][2]*/) {
+                                int rows_per_block, float* __restrict__ ws, float eps) {
   pdl_grid_sync();
   extern __shared__ float sm[];  // [ty][2*C] partials, then [2*C] totals in row 0
+  __shared__ int s_last;
   const int s = blockIdx.y;
+  const int S = gridDim.y, nblk = gridDim.x;
+  int* tickets = reinterpret_cast<int*>(ws);
+  float* fin = ws + GN_TICKETS;
+  float* part = fin + (size_t)S * 64;
   const int row0 = blockIdx.x * rows_per_block;
   const int row1 = min(row0 + rows_per_block, rows_per_stat);
   const int vec = threadIdx.x;
@@ -75,40 +85,56 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long l
     const int g = tid & 31, which = tid >> 5;
     float a = 0.f;
     for (int c = g * cpg; c < (g + 1) * cpg; ++c) a += sm[which * C + c];
-    part[(((long long)s * gridDim.x + blockIdx.x) * 32 + g) * 2 + which] = a;
+    part[(((long long)s * nblk + blockIdx.x) * 32 + g) * 2 + which] = a;
+    __threadfence();
   }
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&tickets[s], 1) == nblk - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // fold the partials of this statistic: thread (slice, pair) sums blocks slice, slice+nsl, ...; then the
+  // slices are added in order.  Both orders are fixed by the launch shape.
+  const int nsl = nthr >> 6;   // >= 1: the block has at least 64 threads
+  if (tid < nsl * 64) {
+    const int pair = tid & 63, slice = tid >> 6;
+    const int g = pair & 31, which = pair >> 5;
+    float a = 0.f;
+    for (int b2 = slice; b2 < nblk; b2 += nsl) a += __ldcg(part + (((long long)s * nblk + b2) * 32 + g) * 2 + which);
+    sm[slice * 64 + pair] = a;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    float su = 0.f, sq2 = 0.f;
+    for (int k = 0; k < nsl; ++k) { su += sm[k * 64 + tid]; sq2 += sm[k * 64 + 32 + tid]; }
+    const float inv_cnt = 1.0f / ((float)cpg * (float)rows_per_stat);
+    const float mean = su * inv_cnt;
+    const float var = fmaxf(sq2 * inv_cnt - mean * mean, 0.f);
+    fin[(size_t)s * 64 + tid] = mean;
+    fin[(size_t)s * 64 + 32 + tid] = rsqrtf(var + eps);
+  }
+  if (tid == 0) tickets[s] = 0;
 }
 
 __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long ld, __nv_bfloat16* __restrict__ y,
                                 long long ldy, int C, int rows_per_stat, int rows_per_block,
-                                const float* __restrict__ part, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, float eps, int silu) {
+                                const float* __restrict__ ws, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, int silu) {
   pdl_grid_sync();
-  extern __shared__ float sm[];  // scale[C], shift[C], stats[64]
+  extern __shared__ float sm[];  // scale[C], shift[C]
   const int s = blockIdx.y;
+  const float* fin = ws + GN_TICKETS + (size_t)s * 64;
   const int row0 = blockIdx.x * rows_per_block;
   const int row1 = min(row0 + rows_per_block, rows_per_stat);
   const int vec = threadIdx.x;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const int nthr = blockDim.x * blockDim.y;
   const int cpg = C / 32;
-  float* st = sm + 2 * C;
-  if (tid < 64) {
-    const int g = tid & 31, which = tid >> 5;
-    float a = 0.f;
-    for (int b = 0; b < (int)gridDim.x; ++b) a += part[(((long long)s * gridDim.x + b) * 32 + g) * 2 + which];
-    st[which * 32 + g] = a;
-  }
-  __syncthreads();
-  const float inv_cnt = 1.0f / ((float)cpg * (float)rows_per_stat);
   for (int c = tid; c < C; c += nthr) {
     const int g = c / cpg;
-    const float mean = st[g] * inv_cnt;
-    const float var = fmaxf(st[32 + g] * inv_cnt - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + eps);
-    const float sc = gamma[c] * rstd;
+    const float sc = gamma[c] * fin[32 + g];
     sm[c] = sc;
-    sm[C + c] = beta[c] - mean * sc;
+    sm[C + c] = beta[c] - fin[g] * sc;
   }
   __syncthreads();
   float sc[8], sh[8];
@@ -146,66 +172,77 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long l
 }
 
 // ---------------------------------------------------------------------------------------------- LayerNorm
-// one warp per row; C multiple of 8, C <= 8*32*MAXV
-template <int MAXV>
+// one warp per ROWS consecutive rows (all their loads are issued before any arithmetic, so a warp keeps
+// ROWS * MAXV 16-byte requests in flight); C multiple of 8, C <= 8*32*MAXV; two-pass statistics in registers
+template <int MAXV, int ROWS>
 __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ld, __nv_bfloat16* __restrict__ y,
                                  long long ldy, int M, int C, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float eps) {
   pdl_grid_sync();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= M) return;
+  const int row0 = warp * ROWS;
+  if (row0 >= M) return;
   const int nvec = C >> 3;
-  float v[MAXV][8];
-  float sum = 0.f;
-  const __nv_bfloat16* xr = x + (long long)warp * ld;
+  uint4 w[ROWS][MAXV];
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
-      const uint4 w = __ldg(reinterpret_cast<const uint4*>(xr + vi * 8));
+  for (int rr = 0; rr < ROWS; ++rr) {
+    const __nv_bfloat16* xr = x + (long long)(row0 + rr) * ld;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = lane + i * 32;
+      w[rr][i] = make_uint4(0u, 0u, 0u, 0u);
+      if (vi < nvec && row0 + rr < M) w[rr][i] = __ldg(reinterpret_cast<const uint4*>(xr + vi * 8));
+    }
+  }
+#pragma unroll
+  for (int rr = 0; rr < ROWS; ++rr) {
+    if (row0 + rr >= M) break;
+    float v[MAXV][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
       float2 f;
-      f = unpack_bf16x2(w.x); v[i][0] = f.x; v[i][1] = f.y;
-      f = unpack_bf16x2(w.y); v[i][2] = f.x; v[i][3] = f.y;
-      f = unpack_bf16x2(w.z); v[i][4] = f.x; v[i][5] = f.y;
-      f = unpack_bf16x2(w.w); v[i][6] = f.x; v[i][7] = f.y;
+      f = unpack_bf16x2(w[rr][i].x); v[i][0] = f.x; v[i][1] = f.y;
+      f = unpack_bf16x2(w[rr][i].y); v[i][2] = f.x; v[i][3] = f.y;
+      f = unpack_bf16x2(w[rr][i].z); v[i][4] = f.x; v[i][5] = f.y;
+      f = unpack_bf16x2(w[rr][i].w); v[i][6] = f.x; v[i][7] = f.y;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) sum += v[i][j];
+      for (int j = 0; j < 8; ++j) sum += v[i][j];   // lanes beyond nvec hold zeros
     }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum / (float)C;
-  float sq = 0.f;
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)C;
+    float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
+    for (int i = 0; i < MAXV; ++i) {
+      if (lane + i * 32 < nvec) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; sq += d * d; }
+        for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; sq += d * d; }
+      }
     }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  const float rstd = rsqrtf(sq / (float)C + eps);
-  __nv_bfloat16* yr = y + (long long)warp * ldy;
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / (float)C + eps);
+    __nv_bfloat16* yr = y + (long long)(row0 + rr) * ldy;
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
-      float o[8];
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
-      o[0] = (v[i][0] - mean) * rstd * g0.x + b0.x; o[1] = (v[i][1] - mean) * rstd * g0.y + b0.y;
-      o[2] = (v[i][2] - mean) * rstd * g0.z + b0.z; o[3] = (v[i][3] - mean) * rstd * g0.w + b0.w;
-      o[4] = (v[i][4] - mean) * rstd * g1.x + b1.x; o[5] = (v[i][5] - mean) * rstd * g1.y + b1.y;
-      o[6] = (v[i][6] - mean) * rstd * g1.z + b1.z; o[7] = (v[i][7] - mean) * rstd * g1.w + b1.w;
-      uint4 w;
-      w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
-      w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
-      *reinterpret_cast<uint4*>(yr + vi * 8) = w;
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        float o[8];
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
+        o[0] = (v[i][0] - mean) * rstd * g0.x + b0.x; o[1] = (v[i][1] - mean) * rstd * g0.y + b0.y;
+        o[2] = (v[i][2] - mean) * rstd * g0.z + b0.z; o[3] = (v[i][3] - mean) * rstd * g0.w + b0.w;
+        o[4] = (v[i][4] - mean) * rstd * g1.x + b1.x; o[5] = (v[i][5] - mean) * rstd * g1.y + b1.y;
+        o[6] = (v[i][6] - mean) * rstd * g1.z + b1.z; o[7] = (v[i][7] - mean) * rstd * g1.w + b1.w;
+        uint4 q;
+        q.x = pack_bf16x2(o[0], o[1]); q.y = pack_bf16x2(o[2], o[3]);
+        q.z = pack_bf16x2(o[4], o[5]); q.w = pack_bf16x2(o[6], o[7]);
+        *reinterpret_cast<uint4*>(yr + vi * 8) = q;
+      }
     }
   }
 }
@@ -221,7 +258,7 @@ static void gn_launch_shape(int num_stats, int rows_per_stat, int C, int sms, di
   const int vecs = C / 8;
   int ty = 512 / vecs; if (ty < 1) ty = 1; if (ty > 32) ty = 32;
   *block = dim3(vecs, ty);
-  int blocks_per_stat = (4 * sms + num_stats - 1) / num_stats;  // ~4 blocks per SM overall
+  int blocks_per_stat = (3 * sms + num_stats - 1) / num_stats;  // ~3 blocks per SM overall
   int rpb = (rows_per_stat + blocks_per_stat - 1) / blocks_per_stat;
   if (rpb < 8 * ty) rpb = 8 * ty;
   blocks_per_stat = (rows_per_stat + rpb - 1) / rpb;
@@ -233,7 +270,7 @@ extern "C" size_t geo4d_groupnorm_workspace_bytes(int num_stats, int rows_per_st
   if (num_stats < 1 || rows_per_stat < 1 || C < 8) return 0;
   dim3 block, grid; int rpb;
   gn_launch_shape(num_stats, rows_per_stat, C, 148, &block, &grid, &rpb);  // upper bound: fewer SMs -> fewer blocks
-  return (size_t)num_stats * grid.x * 64 * sizeof(float);
+  return ((size_t)GN_TICKETS + (size_t)num_stats * 64 + (size_t)num_stats * grid.x * 64) * sizeof(float);
 }
 
 extern "C" int geo4d_groupnorm_silu(const void* x, int64_t ldx, void* y, int64_t ldy, int num_stats,
@@ -241,7 +278,7 @@ extern "C" int geo4d_groupnorm_silu(const void* x, int64_t ldx, void* y, int64_t
                                     int apply_silu, void* workspace, size_t workspace_bytes, g4_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!x || !y || !gamma || !beta || !workspace) { set_last_error("groupnorm: null pointer"); return G4_ERR_BAD_ARG; }
-  if (C % 32 || C % 8 || C > 8 * 1024 || num_stats < 1 || num_stats > 65535 || rows_per_stat < 1) {
+  if (C % 32 || C % 8 || C > 8 * 1024 || num_stats < 1 || num_stats > GN_TICKETS || rows_per_stat < 1) {
     set_last_error("groupnorm: C=%d must be a multiple of 32 and 8 (<=8192); num_stats=%d rows=%d", C, num_stats,
                    rows_per_stat);
     return G4_ERR_BAD_ARG;
@@ -252,10 +289,12 @@ extern "C" int geo4d_groupnorm_silu(const void* x, int64_t ldx, void* y, int64_t
   const int sms = device_sm_count(); if (sms <= 0) return G4_ERR_CUDA;
   dim3 block, grid; int rows_per_block;
   gn_launch_shape(num_stats, rows_per_stat, C, sms > 148 ? 148 : sms, &block, &grid, &rows_per_block);
-  const size_t need = (size_t)num_stats * grid.x * 64 * sizeof(float);
+  const size_t need = ((size_t)GN_TICKETS + (size_t)num_stats * 64 + (size_t)num_stats * grid.x * 64) * sizeof(float);
   if (workspace_bytes < need) { set_last_error("groupnorm: workspace %zu < %zu", workspace_bytes, need); return G4_ERR_WORKSPACE; }
-  const size_t smem_stats = (size_t)block.y * 2 * C * sizeof(float);
-  const size_t smem_apply = (2 * (size_t)C + 64) * sizeof(float);
+  size_t smem_stats = (size_t)block.y * 2 * C * sizeof(float);
+  const size_t fold = (size_t)(block.x * block.y / 64) * 64 * sizeof(float);
+  if (smem_stats < fold) smem_stats = fold;
+  const size_t smem_apply = 2 * (size_t)C * sizeof(float);
   if (smem_stats > 48 * 1024) {
     static bool attr = false;
     if (!attr) {
@@ -265,12 +304,12 @@ extern "C" int geo4d_groupnorm_silu(const void* x, int64_t ldx, void* y, int64_t
     }
   }
   launch_pdl(gn_stats_kernel, dim3(grid), dim3(block), smem_stats, stream, reinterpret_cast<const __nv_bfloat16*>(x), ldx, C, rows_per_stat,
-                                                       rows_per_block, reinterpret_cast<float*>(workspace));
+                                                       rows_per_block, reinterpret_cast<float*>(workspace), eps);
   int rc = check_launch("gn_stats"); if (rc) return rc;
   launch_pdl(gn_apply_kernel, dim3(grid), dim3(block), smem_apply, stream, reinterpret_cast<const __nv_bfloat16*>(x), ldx,
                                                        reinterpret_cast<__nv_bfloat16*>(y), ldy, C, rows_per_stat,
                                                        rows_per_block, reinterpret_cast<const float*>(workspace), gamma,
-                                                       beta, eps, apply_silu);
+                                                       beta, apply_silu);
   return check_launch("gn_apply");
 }
 
@@ -283,14 +322,13 @@ extern "C" int geo4d_layernorm(const void* x, int64_t ldx, void* y, int64_t ldy,
       (reinterpret_cast<uintptr_t>(gamma) & 15) || (reinterpret_cast<uintptr_t>(beta) & 15)) {
     set_last_error("layernorm: pointers must be 16-byte aligned, ld multiple of 8"); return G4_ERR_BAD_ARG;
   }
-  const int warps_per_block = 8;
-  const int grid = (M + warps_per_block - 1) / warps_per_block;
   const int nvec = C / 8;
   const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
-  if (nvec <= 32) launch_pdl(layernorm_kernel<1>, dim3(grid), dim3(256), 0, stream, xp, ldx, yp, ldy, M, C, gamma, beta, eps);
-  else if (nvec <= 64) launch_pdl(layernorm_kernel<2>, dim3(grid), dim3(256), 0, stream, xp, ldx, yp, ldy, M, C, gamma, beta, eps);
-  else if (nvec <= 128) launch_pdl(layernorm_kernel<4>, dim3(grid), dim3(256), 0, stream, xp, ldx, yp, ldy, M, C, gamma, beta, eps);
-  else launch_pdl(layernorm_kernel<8>, dim3(grid), dim3(256), 0, stream, xp, ldx, yp, ldy, M, C, gamma, beta, eps);
+  auto grid_for_rows = [&](int rows_per_warp) { return (M + 8 * rows_per_warp - 1) / (8 * rows_per_warp); };
+  if (nvec <= 32) launch_pdl(layernorm_kernel<1, 4>, dim3(grid_for_rows(4)), dim3(256), 0, stream, xp, ldx, yp, ldy, M, C, gamma, beta, eps);
+  else if (nvec <= 64) launch_pdl(layernorm_kernel<2, 4>, dim3(grid_for_rows(4)), dim3(256), 0, stream, xp, ldx, yp, ldy, M, C, gamma, beta, eps);
+  else if (nvec <= 128) launch_pdl(layernorm_kernel<4, 2>, dim3(grid_for_rows(2)), dim3(256), 0, stream, xp, ldx, yp, ldy, M, C, gamma, beta, eps);
+  else launch_pdl(layernorm_kernel<8, 1>, dim3(grid_for_rows(1)), dim3(256), 0, stream, xp, ldx, yp, ldy, M, C, gamma, beta, eps);
   return check_launch("layernorm");
 }

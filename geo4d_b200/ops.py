@@ -155,7 +155,7 @@ def _gn_workspace(device, num_stats: int, rows_per_stat: int, Cc: int) -> torch.
     need = int(f(num_stats, rows_per_stat, Cc)) // 4
     ws = _gn_ws.get(device)
     if ws is None or ws.numel() < need:
-        ws = torch.empty(max(need, 1 << 18), device=device, dtype=torch.float32)
+        ws = torch.zeros(max(need, 1 << 18), device=device, dtype=torch.float32)  # tickets start at zero
         _gn_ws[device] = ws
     return ws
 

@@ -40,10 +40,14 @@ const char* geo4d_last_error(void);
 int geo4d_device_supported(void);
 /* Number of kernels this library has launched (or recorded into a CUDA graph) in this process. */
 uint64_t geo4d_launch_count(void);
-/* Debug aid: when non-null, every geo4d_tap_gemm launch writes 8 %globaltimer stamps per CTA into
- * buf[grid][8] (entry, setup done, first operands landed, first tile's MMAs issued, first accumulator
+/* Debug aid: when non-null, every geo4d_tap_gemm launch writes up to 16 %globaltimer stamps per CTA into
+ * buf[grid][16] (entry, setup done, first operands landed, first tile's MMAs issued, first accumulator
  * ready, first / last epilogue done, exit).  Pass NULL to switch it off (the default). */
 void geo4d_debug_gemm_trace(void* buf);
+/* Debug aid: non-zero forces the direct (per-thread) store epilogue instead of shared memory + TMA stores. */
+void geo4d_debug_gemm_direct_store(int on);
+/* Debug aid: -1 = cost model (default), 0 = never pair CTAs (cta_group::1 only), 1 = always pair when legal. */
+void geo4d_debug_gemm_pair_mode(int mode);
 
 /* ------------------------------------------------------------------------------------------------
  * Tap-GEMM on tcgen05 tensor cores (TMA -> shared memory -> tcgen05.mma -> TMEM -> epilogue).
@@ -114,7 +118,10 @@ int geo4d_temporal_attention(const void* q, const void* k, const void* v, int64_
                              int B, int T, int HW, int heads, float scale, g4_stream_t stream);
 
 /* GroupNorm(32) [+SiLU] over `rows_per_stat` consecutive rows per statistic (basics.py:76-87,
- * openaimodel3d.py:151-155,175-180,256-266; attention.py:265,331; ae_modules.py:14-15). */
+ * openaimodel3d.py:151-155,175-180,256-266; attention.py:265,331; ae_modules.py:14-15).
+ * `workspace` (geo4d_groupnorm_workspace_bytes) holds per-block partial sums and the completion tickets of
+ * the statistics pass: its first 16 KiB must be ZERO before the first call (allocate it zero-filled once);
+ * every call leaves them zero again, so one buffer serves any number of calls on a stream.  num_stats <= 4096. */
 size_t geo4d_groupnorm_workspace_bytes(int num_stats, int rows_per_stat, int C);
 int geo4d_groupnorm_silu(const void* x, int64_t ldx, void* y, int64_t ldy, int num_stats, int rows_per_stat,
                          int C, const float* gamma, const float* beta, float eps, int apply_silu,

@@ -181,6 +181,29 @@ def test_fused_small_parameter_kernel_gradients_match_autograd(cuda_device, monk
     focal parameterisations, temporal-smoothing and trajectory-prior pose terms) vs torch autograd on the same
     dense-kernel reductions.  With every term active from iteration 0 the first Adam moment is 0.1 * gradient,
     so the kernel's gradient can be read back exactly and compared tensor by tensor."""
+    # The phase-B initialisation sits exactly on the kinks of the objective (the LAD fit zeroes d loss/d(s, t);
+    # align_origin makes the first frame's relative pose the identity, where ||R - I|| and ||t|| are not
+    # differentiable), so gradients there are decided by rounding.  Move off the kinks, identically in both modes.
+    from geo4d_b200.cloud_opt import LightPointCloudGroupOptimizer as Opt
+    orig_traj, orig_st = Opt._set_traj, Opt._set_st_depth
+
+    def set_traj(self):
+        out = orig_traj(self)
+        with torch.no_grad():
+            G = self.traj_align_poses.shape[0]
+            bump = torch.linspace(-1.0, 1.0, G * 8, device=self.traj_align_poses.device).reshape(G, 8)
+            self.traj_align_poses.add_(0.02 * bump)
+        return out
+
+    def set_st(self):
+        out = orig_st(self)
+        with torch.no_grad():
+            self.s_depth.mul_(1.05)
+            self.t_depth.add_(0.02)
+        return out
+
+    monkeypatch.setattr(Opt, "_set_traj", set_traj)
+    monkeypatch.setattr(Opt, "_set_st_depth", set_st)
     a, _ = _run_small("1", monkeypatch, cuda_device, niter=1, start_b=0)
     f, _ = _run_small("0", monkeypatch, cuda_device, niter=1, start_b=0)
     assert list(a.valid_traj_group_list) == list(f.valid_traj_group_list) and len(a.valid_traj_group_list) > 0
@@ -198,7 +221,7 @@ def test_fused_small_parameter_kernel_gradients_match_autograd(cuda_device, monk
         scale = float(ref.abs().max())
         assert scale > 0, name
         err = float((got[name] - ref).abs().max()) / scale
-        assert err < 2e-3, (name, err, ref, got[name])
+        assert err < 2e-3, (name, err, (got[name] - ref).abs().max(0).values if ref.dim() > 1 else (got[name] - ref))
 
 
 def test_fused_small_parameter_kernel_trajectory(cuda_device, monkeypatch):

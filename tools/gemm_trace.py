@@ -11,7 +11,7 @@ dev = torch.device("cuda")
 lib = ops.lib()
 
 def trace(fn, label, flops):
-    buf = torch.zeros(148, 8, dtype=torch.int64, device=dev)
+    buf = torch.zeros(148, 16, dtype=torch.int64, device=dev)
     for _ in range(3): fn()
     torch.cuda.synchronize()
     lib.geo4d_debug_gemm_trace(ops._vp(buf))
@@ -26,6 +26,9 @@ def trace(fn, label, flops):
     def med(c):
         v = rel[:, c][t[:, c] > 0]
         return float(v.median()) if len(v) else float("nan")
+    def cd(a, b):
+        ok = (t[:, a] > 0) & (t[:, b] > 0)
+        return float((t[ok][:, a] - t[ok][:, b]).median()) if bool(ok.any()) else float("nan")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(50): fn()
@@ -33,7 +36,7 @@ def trace(fn, label, flops):
     us = e0.elapsed_time(e1) * 1e3 / 50
     print(f"{label:44s} {us:7.1f} us/launch {flops / us * 1e-6:7.1f} TF/s | ctas {int(used.sum()):3d} entry-spread {float(rel[:,0].max()):5.1f} "
           f"setup {med(1):5.1f} first-operands {med(2):5.1f} tile0-mma-issued {med(3):5.1f} acc0-ready {med(4):5.1f} "
-          f"epi0-done {med(5):5.1f} last-epi {med(6):5.1f} exit med {med(7):5.1f} max {float(rel[:,7].max()):5.1f}", flush=True)
+          f"epi0-done {med(5):5.1f} last-epi {med(6):5.1f} exit med {med(7):5.1f} max {float(rel[:,7].max()):5.1f} | chunk0 clk: ld {cd(8,13):5.0f} math {cd(9,8):5.0f} barA {cd(10,9):5.0f} sts+fence {cd(11,10):5.0f} barB+tma {cd(12,11):5.0f}", flush=True)
 
 def lin(M, K, N, act=0, residual=False, bias=True):
     x = torch.randn(M, K, device=dev).bfloat16()
@@ -54,6 +57,10 @@ def tconv(B, T, HW, C):
     b = torch.randn(C, device=dev)
     trace(lambda: ops.temporal_conv3(x, B, T, HW, w, b), f"temporal_conv3 {T}x{HW} {C}", 2.0 * B * T * HW * 3 * C * C)
 
+MODE = os.environ.get("DIRECT", "0")
+lib.geo4d_debug_gemm_direct_store(int(MODE))
+lib.geo4d_debug_gemm_pair_mode(int(os.environ.get("PAIR", "-1")))
+print("direct_store =", MODE)
 lin(40960, 320, 320); lin(40960, 320, 320, residual=True); lin(40960, 320, 960, bias=False); lin(40960, 320, 2560, act=2); lin(40960, 1280, 320, residual=True)
 lin(10240, 640, 640); lin(10240, 640, 1920, bias=False); lin(10240, 640, 5120, act=2); lin(10240, 2560, 640, residual=True)
 lin(2560, 1280, 1280); lin(2560, 1280, 3840, bias=False); lin(2560, 1280, 10240, act=2); lin(2560, 5120, 1280, residual=True)
