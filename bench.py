@@ -41,6 +41,55 @@ def peaks():
     return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback")
 
 
+def kernel_rooflines(dev, pk):
+    """Live per-kernel numbers for the dominant kernel (tap_gemm_kernel) on its heaviest U-Net shapes and for the
+    attention kernel: each launch is timed GPU-bound (20 launches in a CUDA graph, CUDA events on the launching
+    stream) and set against the measured dense-bf16 burst peak (a kernel timed alone)."""
+    import torch
+    from geo4d_b200 import ops
+
+    def gtime(fn, n=20):
+        fn()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                for _ in range(n):
+                    fn()
+            g.replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(side)
+            for _ in range(3):
+                g.replay()
+            e1.record(side)
+            e1.synchronize()
+        torch.cuda.current_stream().wait_stream(side)
+        return e0.elapsed_time(e1) * 1e-3 / (3 * n)
+
+    bf = lambda *sh: torch.randn(*sh, device=dev).bfloat16()
+    out = []
+
+    def add(name, flops, sec, launches_per_step):
+        ach = flops / sec * 1e-12
+        out.append({"kernel": name, "us": round(sec * 1e6, 2), "achieved": round(ach, 1), "unit": "TFLOP/s",
+                    "peak": pk["bf16_burst"], "frac": round(ach / pk["bf16_burst"], 3),
+                    "launches_per_unet_step": launches_per_step})
+
+    x = bf(40960, 320); w9 = bf(9, 320, 320); b = torch.randn(320, device=dev); o = torch.empty(40960, 320, device=dev, dtype=torch.bfloat16)
+    add("tap_gemm conv3x3 16x40x64 320->320", 2.0 * 40960 * 2880 * 320, gtime(lambda: ops.conv3x3(x, 16, 40, 64, w9, b, out=o)), 7)
+    x1 = bf(10240, 640); w1 = bf(9, 640, 640); b1 = torch.randn(640, device=dev); o1 = torch.empty(10240, 640, device=dev, dtype=torch.bfloat16)
+    add("tap_gemm conv3x3 16x20x32 640->640", 2.0 * 10240 * 5760 * 640, gtime(lambda: ops.conv3x3(x1, 16, 20, 32, w1, b1, out=o1)), 6)
+    wl = bf(320, 320)
+    add("tap_gemm linear 40960x320->320 (+bias)", 2.0 * 40960 * 320 * 320, gtime(lambda: ops.linear(x, wl, b, out=o)), 45)
+    wg = bf(2560, 320); bg = torch.randn(2560, device=dev); og = torch.empty(40960, 1280, device=dev, dtype=torch.bfloat16)
+    add("tap_gemm linear 40960x320->2560 GEGLU", 2.0 * 40960 * 320 * 2560, gtime(lambda: ops.linear(x, wg, bg, act=ops.ACT_GEGLU, out=og)), 10)
+    qkv = bf(40960, 960)
+    add("attn_fwd B16 H5 L2560 d64", 4.0 * 16 * 5 * 2560 * 2560 * 64,
+        gtime(lambda: ops.attention(qkv[:, :320], qkv[:, 320:640], qkv[:, 640:], o, 16, 5, 2560, 2560)), 5)
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -241,6 +290,10 @@ def main():
                 "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
                 "peak_source": pk["source"] + " (sustained: timed inside a long step)", "traffic": None,
                 "algorithmic_tflop_per_launch": tflop, "ms_per_launch": unet_ms}
+        try:
+            roof["kernels"] = kernel_rooflines(dev, pk)
+        except Exception as ex:  # pragma: no cover
+            roof["kernels"] = {"error": repr(ex)}
     value = T * args.steps / (ms * 1e-3)
     line = {"metric": "4D-recon frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -248,7 +301,8 @@ def main():
             "config": {"workload": f"{T}f {H}x{W}, {args.ddim_steps}-step DDIM (cfg 1, eta 0, uniform_trailing), "
                                    f"{len(windows)} window(s) stride 8, {args.align_iters}-iter alignment",
                        "l2": "weights 2.9 GB + activations >> 126 MB L2 (no flush needed)",
-                       "weights": "seeded synthetic", "parallelism": f"window-parallel x{world}"},
+                       "weights": "seeded synthetic", "parallelism": f"window-parallel x{world}",
+                       "gemm_autotune": f"{len(ops.tuned_configs())} shapes pinned during warm-up"},
             "e2e": {"value": T * args.steps / (ms_e2e * 1e-3), "unit": "frames/s",
                     "h2d_bytes_per_step": video_host.numel() * 4, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clk, "roofline": roof,

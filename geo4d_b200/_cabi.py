@@ -28,6 +28,7 @@ class GemmDesc(C.Structure):
         ("bias", C.c_void_p), ("row_bias", C.c_void_p), ("row_bias_ld", C.c_int64),
         ("rows_per_bias", C.c_int), ("act", C.c_int),
         ("residual", C.c_void_p), ("ldr", C.c_int64),
+        ("tile_n", C.c_int32), ("cta_pair", C.c_int32),
     ]
 
 

@@ -228,12 +228,14 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const bool row_ok = (r < rows_in_tile) && (x < args.W) && (y < args.H) && (n < args.N);
       const long long row = ((long long)n * args.H + y) * args.W + x;
       const int col_base = nt * BLOCK_N;
-      // chunks of this warp: c = half, half+2, ... while the chunk starts inside n_out
+      // The two halves run decoupled (no block-wide barrier): half h owns the chunks of parity (h + it) & 1, so
+      // an odd chunk count (BLOCK_N = 160) balances over two tiles.  c = par, par+2, ... inside n_out.
+      const int par = (half + it) & 1;
       int my_chunks = 0;
-      for (int c = half; c < n_chunks && col_base + c * acc_cols < args.n_out; c += 2) ++my_chunks;
+      for (int c = par; c < n_chunks && col_base + c * acc_cols < args.n_out; c += 2) ++my_chunks;
 
-      // Stage the per-column additive terms (bias + the emb row of this tile) in shared memory while the
-      // MMAs of this tile are still running: the epilogue then never waits on a global load for them.
+      // Stage the per-column additive terms (bias + the emb row of this tile) of this half's chunks in shared
+      // memory while the MMAs of this tile are still running: the epilogue then never waits on a global load.
       float* sb = s_bias + acc * 256;
       bool rb_in_smem = false;
       {
@@ -246,16 +248,18 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           rb_row = first / args.rows_per_bias;
           rb_in_smem = (last / args.rows_per_bias) == rb_row;
         }
-        if (et < BLOCK_N) {
-          const int col = col_base + et;
+        const int ht = (e & 3) * 32 + lane;              // 0..127 within the half
+        if (ht < my_chunks * acc_cols) {
+          const int lc = (par + 2 * (ht / acc_cols)) * acc_cols + ht % acc_cols;   // column inside the tile
+          const int col = col_base + lc;
           float bv = 0.f;
           if (col < args.n_out) {
             if (args.bias) bv = __ldg(args.bias + col);
             if (rb_in_smem) bv += __ldg(args.row_bias + rb_row * args.row_bias_ld + col);
           }
-          sb[et] = bv;
+          sb[lc] = bv;
         }
-        named_bar_sync(1, 256);
+        named_bar_sync(bar_id, 128);
       }
 
       // residual of the first chunk: requested before the accumulator is ready, so its latency hides
@@ -266,11 +270,11 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (args.residual && row_ok && my_chunks > 0) {
         rrow = reinterpret_cast<const __nv_bfloat16*>(args.residual) + row * args.ldr + col_base;
         res_vec = ((reinterpret_cast<uintptr_t>(rrow) & 31) == 0) && ((args.ldr & 15) == 0);
-        if (res_vec && col_base + half * 32 + 32 <= args.n_out) {
+        if (res_vec && col_base + par * 32 + 32 <= args.n_out) {
           uint32_t(&lo)[8] = *reinterpret_cast<uint32_t(*)[8]>(&rr[0]);
           uint32_t(&hi)[8] = *reinterpret_cast<uint32_t(*)[8]>(&rr[8]);
-          ldg256(rrow + half * 32, lo);
-          ldg256(rrow + half * 32 + 16, hi);
+          ldg256(rrow + par * 32, lo);
+          ldg256(rrow + par * 32 + 16, hi);
         }
       }
 
@@ -285,7 +289,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
 #pragma unroll 1
       for (int ci = 0; ci < my_chunks; ++ci) {
-        const int c = half + 2 * ci;
+        const int c = par + 2 * ci;
         const int col0 = col_base + c * acc_cols;              // first accumulator column (B-row space)
         const int scol0 = (args.act == G4_ACT_GEGLU) ? (col0 >> 1) : col0;   // first stored column
         const int n_store = (args.act == G4_ACT_GEGLU) ? (args.n_out >> 1) : args.n_out;
@@ -373,17 +377,30 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (it == 0 && ci == 0 && et == 0) trace_stamp(args, 9);
           {
             uint8_t* slab = my_slabs + (kk % Cfg::NSLAB) * Cfg::SLAB_BYTES;
-            if (issuer) bulk_wait_read<Cfg::NSLAB - 1>();   // the store that last used this slab has drained it
-            named_bar_sync(bar_id, 128);
             uint4* rowp = reinterpret_cast<uint4*>(slab + r * 64);
+            if (Cfg::NSLAB >= 2) {
+              // Two-slab ring, ONE barrier per chunk: the barrier of chunk k-1 already told everybody that this
+              // slab is free, because the issuer waits for all earlier stores (<= k-2 at that point) to have
+              // drained their slabs before it joins a barrier.
 #pragma unroll
-            for (int j = 0; j < 4; ++j) rowp[(uint32_t)j ^ sw] = w[j];
-            fence_proxy_async_smem();
-            named_bar_sync(bar_id, 128);
+              for (int j = 0; j < 4; ++j) rowp[(uint32_t)j ^ sw] = w[j];
+              fence_proxy_async_smem();
+              if (issuer) bulk_wait_read<0>();
+              named_bar_sync(bar_id, 128);
+            } else {
+              if (issuer) bulk_wait_read<0>();   // the store that last used this slab has drained it
+              named_bar_sync(bar_id, 128);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) rowp[(uint32_t)j ^ sw] = w[j];
+              fence_proxy_async_smem();
+              named_bar_sync(bar_id, 128);
+            }
+            if (it == 0 && ci == 0 && et == 0) trace_stamp(args, 11);
             if (issuer) {
               tma_store_4d(&tmC, slab, scol0, x0, y0, n0);
               bulk_commit();
             }
+            if (it == 0 && ci == 0 && et == 0) trace_stamp(args, 12);
           }
           ++kk;
         } else if (row_ok) {
@@ -533,14 +550,20 @@ extern "C" int geo4d_tap_gemm(const g4_gemm_desc* d, g4_stream_t stream_) {
                               ((d->N + d->box_n - 1) / d->box_n);
     const long long k_iters = (long long)d->num_taps * (d->K / 64);
     const int cands[5] = {256, 160, 128, 64, 32};
-    const bool pair_ok = !d->b_batched && sms >= 2 && g_pair_mode != 0;
+    const int pair_mode = d->cta_pair == 1 ? 0 : (d->cta_pair == 2 ? 1 : g_pair_mode);
+    const bool pair_ok = !d->b_batched && sms >= 2 && pair_mode != 0;
+    if (d->cta_pair == 2 && !pair_ok) { set_last_error("tap_gemm: cta_pair=2 is not legal here (batched B or < 2 SMs)"); return G4_ERR_BAD_ARG; }
+    if (d->tile_n != 0 && d->tile_n != 32 && d->tile_n != 64 && d->tile_n != 128 && d->tile_n != 160 && d->tile_n != 256) {
+      set_last_error("tap_gemm: tile_n=%d (0, 32, 64, 128, 160 or 256)", d->tile_n); return G4_ERR_BAD_ARG;
+    }
     double best = 0;
     for (int pass = 0; pass < 2; ++pass) {
       const bool tw = pass == 0;
       if (tw && !pair_ok) continue;
-      if (!tw && pair_ok && g_pair_mode == 1) continue;
+      if (!tw && pair_ok && pair_mode == 1) continue;
       for (int ci = 0; ci < 5; ++ci) {
         const int c = cands[ci];
+        if (d->tile_n != 0 && c != d->tile_n) continue;
         if (d->act == G4_ACT_GEGLU && (c == 160 || c == 32 || n % c)) continue;
         if (c > 32 && n <= c / 2 && c != 64) continue;                 // do not pad tiny outputs to wide tiles
         const long long n_tiles = (n + c - 1) / c;
@@ -555,7 +578,10 @@ extern "C" int geo4d_tap_gemm(const g4_gemm_desc* d, g4_stream_t stream_) {
         if (bn == 0 || cost < best) { bn = c; best = cost; two = tw; }
       }
     }
-    if (bn == 0) bn = (d->act == G4_ACT_GEGLU) ? 64 : 32;
+    if (bn == 0) {
+      if (d->tile_n != 0) { set_last_error("tap_gemm: tile_n=%d is not legal for n_out=%d act=%d", d->tile_n, n, d->act); return G4_ERR_BAD_ARG; }
+      bn = (d->act == G4_ACT_GEGLU) ? 64 : 32;
+    }
   }
 
   CUtensorMap tmA, tmB, tmC;

@@ -171,6 +171,157 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long l
   }
 }
 
+// Single-launch variant: statistics, a per-statistic grid barrier, then the apply pass (which re-reads x,
+// normally still in L2).  Launched cooperatively so that all blocks are co-resident; the barrier is
+// "last block to arrive folds + publishes, everybody else polls one flag word".  Counters live in the first
+// 16 KiB of the workspace (tickets | flags | leave counters | unused) and are back to zero when the kernel ends.
+__global__ void gn_fused_kernel(const __nv_bfloat16* __restrict__ x, long long ld, __nv_bfloat16* __restrict__ y,
+                                long long ldy, int C, int rows_per_stat, int rows_per_block, float* __restrict__ ws,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu) {
+  pdl_grid_sync();
+  extern __shared__ float sm[];  // [ty][2*C] partials / fold scratch, later scale[C] shift[C]
+  __shared__ int s_last;
+  const int s = blockIdx.y;
+  const int S = gridDim.y, nblk = gridDim.x;
+  int* tickets = reinterpret_cast<int*>(ws);
+  int* flags = tickets + GN_TICKETS / 4;
+  int* leaves = tickets + GN_TICKETS / 2;
+  float* fin = ws + GN_TICKETS;
+  float* part = fin + (size_t)S * 64;
+  const int row0 = blockIdx.x * rows_per_block;
+  const int row1 = min(row0 + rows_per_block, rows_per_stat);
+  const int vec = threadIdx.x;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nthr = blockDim.x * blockDim.y;
+  const int cpg = C / 32;
+  const int step = blockDim.y;
+  const __nv_bfloat16* xb = x + ((long long)s * rows_per_stat) * ld + vec * 8;
+  {
+    float sum[8], sq[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sum[j] = 0.f; sq[j] = 0.f; }
+    for (int r0 = row0 + threadIdx.y; r0 < row1; r0 += 4 * step) {
+      uint4 w[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        w[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (r0 + u * step < row1) w[u] = __ldg(reinterpret_cast<const uint4*>(xb + (long long)(r0 + u * step) * ld));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float2 f;
+        f = unpack_bf16x2(w[u].x); sum[0] += f.x; sq[0] += f.x * f.x; sum[1] += f.y; sq[1] += f.y * f.y;
+        f = unpack_bf16x2(w[u].y); sum[2] += f.x; sq[2] += f.x * f.x; sum[3] += f.y; sq[3] += f.y * f.y;
+        f = unpack_bf16x2(w[u].z); sum[4] += f.x; sq[4] += f.x * f.x; sum[5] += f.y; sq[5] += f.y * f.y;
+        f = unpack_bf16x2(w[u].w); sum[6] += f.x; sq[6] += f.x * f.x; sum[7] += f.y; sq[7] += f.y * f.y;
+      }
+    }
+    float* mine = sm + (size_t)threadIdx.y * 2 * C;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mine[vec * 8 + j] = sum[j];
+      mine[C + vec * 8 + j] = sq[j];
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < 2 * C; c += nthr) {
+    float a = 0.f;
+    for (int yy = 0; yy < (int)blockDim.y; ++yy) a += sm[(size_t)yy * 2 * C + c];
+    sm[c] = a;
+  }
+  __syncthreads();
+  if (tid < 64) {
+    const int g = tid & 31, which = tid >> 5;
+    float a = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) a += sm[which * C + c];
+    part[(((long long)s * nblk + blockIdx.x) * 32 + g) * 2 + which] = a;
+    __threadfence();
+  }
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&tickets[s], 1) == nblk - 1) ? 1 : 0;
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    const int nsl = nthr >> 6;
+    if (tid < nsl * 64) {
+      const int pair = tid & 63, slice = tid >> 6;
+      const int g = pair & 31, which = pair >> 5;
+      float a = 0.f;
+      for (int b2 = slice; b2 < nblk; b2 += nsl) a += __ldcg(part + (((long long)s * nblk + b2) * 32 + g) * 2 + which);
+      sm[slice * 64 + pair] = a;
+    }
+    __syncthreads();
+    if (tid < 32) {
+      float su = 0.f, sq2 = 0.f;
+      for (int k = 0; k < nsl; ++k) { su += sm[k * 64 + tid]; sq2 += sm[k * 64 + 32 + tid]; }
+      const float inv_cnt = 1.0f / ((float)cpg * (float)rows_per_stat);
+      const float mean = su * inv_cnt;
+      const float var = fmaxf(sq2 * inv_cnt - mean * mean, 0.f);
+      fin[(size_t)s * 64 + tid] = mean;
+      fin[(size_t)s * 64 + 32 + tid] = rsqrtf(var + eps);
+      __threadfence();
+    }
+    __syncthreads();
+    if (tid == 0) atomicExch(&flags[s], 1);
+  } else if (tid == 0) {
+    long long t0 = clock64();
+    while (*reinterpret_cast<volatile int*>(&flags[s]) == 0) {
+      __nanosleep(40);
+      if (clock64() - t0 > G4_MBAR_TIMEOUT_CYCLES) {
+        printf("g4: groupnorm grid barrier timeout (block %d,%d)\n", (int)blockIdx.x, (int)blockIdx.y);
+        __trap();
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  // ---- apply
+  for (int c = tid; c < C; c += nthr) {
+    const int g = c / cpg;
+    const float sc = gamma[c] * __ldcg(fin + (size_t)s * 64 + 32 + g);
+    sm[c] = sc;
+    sm[C + c] = beta[c] - __ldcg(fin + (size_t)s * 64 + g) * sc;
+  }
+  __syncthreads();
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = sm[vec * 8 + j]; sh[j] = sm[C + vec * 8 + j]; }
+  __nv_bfloat16* yb = y + ((long long)s * rows_per_stat) * ldy + vec * 8;
+  for (int r0 = row0 + threadIdx.y; r0 < row1; r0 += 4 * step) {
+    uint4 w[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (r0 + u * step < row1) w[u] = __ldg(reinterpret_cast<const uint4*>(xb + (long long)(r0 + u * step) * ld));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (r0 + u * step < row1) {
+        float v[8];
+        float2 f;
+        f = unpack_bf16x2(w[u].x); v[0] = f.x; v[1] = f.y;
+        f = unpack_bf16x2(w[u].y); v[2] = f.x; v[3] = f.y;
+        f = unpack_bf16x2(w[u].z); v[4] = f.x; v[5] = f.y;
+        f = unpack_bf16x2(w[u].w); v[6] = f.x; v[7] = f.y;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[j] = v[j] * sc[j] + sh[j];
+          if (silu) v[j] = silu_f(v[j]);
+        }
+        uint4 o;
+        o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+        o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(yb + (long long)(r0 + u * step) * ldy) = o;
+      }
+    }
+  }
+  // ---- leave: the last block of this statistic puts the counters back to zero
+  __syncthreads();
+  if (tid == 0 && atomicAdd(&leaves[s], 1) == nblk - 1) {
+    tickets[s] = 0;
+    flags[s] = 0;
+    leaves[s] = 0;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- LayerNorm
 // one warp per ROWS consecutive rows (all their loads are issued before any arithmetic, so a warp keeps
 // ROWS * MAXV 16-byte requests in flight); C multiple of 8, C <= 8*32*MAXV; two-pass statistics in registers
@@ -248,6 +399,7 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long 
 }
 
 int device_sm_count();
+static bool g_gn_two_kernels = false;   // debug switch: keep statistics and apply in separate launches
 
 }  // namespace g4
 
@@ -265,6 +417,8 @@ static void gn_launch_shape(int num_stats, int rows_per_stat, int C, int sms, di
   *rows_per_block = rpb;
   *grid = dim3(blocks_per_stat, num_stats);
 }
+
+extern "C" void geo4d_debug_groupnorm_two_kernels(int on) { g4::g_gn_two_kernels = on != 0; }
 
 extern "C" size_t geo4d_groupnorm_workspace_bytes(int num_stats, int rows_per_stat, int C) {
   if (num_stats < 1 || rows_per_stat < 1 || C < 8) return 0;
@@ -289,20 +443,49 @@ extern "C" int geo4d_groupnorm_silu(const void* x, int64_t ldx, void* y, int64_t
   const int sms = device_sm_count(); if (sms <= 0) return G4_ERR_CUDA;
   dim3 block, grid; int rows_per_block;
   gn_launch_shape(num_stats, rows_per_stat, C, sms > 148 ? 148 : sms, &block, &grid, &rows_per_block);
-  const size_t need = ((size_t)GN_TICKETS + (size_t)num_stats * 64 + (size_t)num_stats * grid.x * 64) * sizeof(float);
-  if (workspace_bytes < need) { set_last_error("groupnorm: workspace %zu < %zu", workspace_bytes, need); return G4_ERR_WORKSPACE; }
   size_t smem_stats = (size_t)block.y * 2 * C * sizeof(float);
   const size_t fold = (size_t)(block.x * block.y / 64) * 64 * sizeof(float);
   if (smem_stats < fold) smem_stats = fold;
   const size_t smem_apply = 2 * (size_t)C * sizeof(float);
-  if (smem_stats > 48 * 1024) {
-    static bool attr = false;
-    if (!attr) {
-      cudaError_t e = cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-      if (e != cudaSuccess) { set_last_error("groupnorm: smem attr: %s", cudaGetErrorString(e)); return G4_ERR_CUDA; }
-      attr = true;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e != cudaSuccess) { set_last_error("groupnorm: smem attr: %s", cudaGetErrorString(e)); return G4_ERR_CUDA; }
+    attr = true;
+  }
+  // single cooperative launch when every block can be resident at once (always true for the U-Net shapes)
+  if (!g_gn_two_kernels && num_stats <= GN_TICKETS / 4) {
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_kernel, (int)(block.x * block.y), smem_stats);
+    if (e == cudaSuccess && per_sm > 0) {
+      const long long cap = (long long)per_sm * sms;
+      dim3 g2 = grid;
+      int rpb2 = rows_per_block;
+      if ((long long)g2.x * g2.y > cap && cap >= num_stats) {
+        g2.x = (unsigned)(cap / num_stats);
+        rpb2 = (rows_per_stat + (int)g2.x - 1) / (int)g2.x;
+        g2.x = (unsigned)((rows_per_stat + rpb2 - 1) / rpb2);
+      }
+      if ((long long)g2.x * g2.y <= cap) {
+        const size_t need2 = ((size_t)GN_TICKETS + (size_t)num_stats * 64 + (size_t)num_stats * g2.x * 64) * sizeof(float);
+        if (workspace_bytes < need2) { set_last_error("groupnorm: workspace %zu < %zu", workspace_bytes, need2); return G4_ERR_WORKSPACE; }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = g2; cfg.blockDim = block; cfg.dynamicSmemBytes = smem_stats; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeCooperative;
+        at[0].val.cooperative = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, gn_fused_kernel, reinterpret_cast<const __nv_bfloat16*>(x), (long long)ldx,
+                               reinterpret_cast<__nv_bfloat16*>(y), (long long)ldy, C, rows_per_stat, rpb2,
+                               reinterpret_cast<float*>(workspace), gamma, beta, eps, apply_silu);
+        if (e == cudaSuccess) return check_launch("gn_fused");
+        (void)cudaGetLastError();   // fall through to the two-kernel path
+      }
     }
   }
+  const size_t need = ((size_t)GN_TICKETS + (size_t)num_stats * 64 + (size_t)num_stats * grid.x * 64) * sizeof(float);
+  if (workspace_bytes < need) { set_last_error("groupnorm: workspace %zu < %zu", workspace_bytes, need); return G4_ERR_WORKSPACE; }
   launch_pdl(gn_stats_kernel, dim3(grid), dim3(block), smem_stats, stream, reinterpret_cast<const __nv_bfloat16*>(x), ldx, C, rows_per_stat,
                                                        rows_per_block, reinterpret_cast<float*>(workspace), eps);
   int rc = check_launch("gn_stats"); if (rc) return rc;

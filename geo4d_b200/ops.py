@@ -7,6 +7,7 @@ enqueue on torch's current stream and never synchronise.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from functools import lru_cache
 from typing import Optional, Sequence, Tuple
 
@@ -76,8 +77,95 @@ def tap_gemm(a: torch.Tensor, K: int, W: int, H: int, N: int, strides: Tuple[int
     d.act = act
     d.residual = _ptr(residual)
     d.ldr = ldr
-    check(lib().geo4d_tap_gemm(C.byref(d), C.c_void_p(_stream())), "geo4d_tap_gemm")
+    if _FORCE_TILE is not None:
+        d.tile_n, d.cta_pair = _FORCE_TILE
+    elif _AUTOTUNE:
+        key = (K, W, H, N, bw, bh, bn, len(taps), n_out, int(b_batched), d.out_fp32, act, bias is not None,
+               row_bias is not None, residual is not None)
+        cfg = _TUNED.get(key)
+        if cfg is None and not torch.cuda.is_current_stream_capturing():
+            cfg = _autotune(d, key, out, residual)
+        if cfg is not None:
+            d.tile_n, d.cta_pair = cfg
+    rc = lib().geo4d_tap_gemm(C.byref(d), C.c_void_p(_stream()))
+    if rc != 0 and _FORCE_TILE is not None:    # a forced configuration that is not legal for this shape: library's choice
+        d.tile_n, d.cta_pair = 0, 0
+        rc = lib().geo4d_tap_gemm(C.byref(d), C.c_void_p(_stream()))
+    check(rc, "geo4d_tap_gemm")
     return out
+
+
+# ---------------------------------------------------------------------------------------------- autotuning
+# The tile shape (tile_n, single CTA vs CTA pair) does not change the result of a tap-GEMM, only its speed, and
+# the best choice depends on the interplay of L2 bandwidth, epilogue cost and wave quantisation.  So the first
+# time a shape is seen (outside CUDA-graph capture) every legal configuration is timed on scratch outputs with a
+# small CUDA graph (GPU-bound, no launch gaps) and the winner is pinned for the rest of the process.
+# GEO4D_AUTOTUNE=0 leaves the choice to the library's cost model.
+_AUTOTUNE = os.environ.get("GEO4D_AUTOTUNE", "1") != "0"
+_TUNED: dict = {}
+_TUNE_LOG: list = []
+_FORCE_TILE: Optional[Tuple[int, int]] = None   # (tile_n, cta_pair) for every launch; tests and experiments only
+
+
+def tuned_configs():
+    """[(key, (tile_n, cta_pair), {candidate: microseconds})] for every shape tuned so far."""
+    return list(_TUNE_LOG)
+
+
+def _autotune(d: GemmDesc, key, out: torch.Tensor, residual: Optional[torch.Tensor]):
+    dev = out.device
+    scratch = torch.empty_strided(out.shape, out.stride(), device=dev, dtype=out.dtype)
+    res = None
+    if residual is not None:
+        res = torch.zeros_like(residual)
+    t = GemmDesc()
+    C.memmove(C.byref(t), C.byref(d), C.sizeof(GemmDesc))
+    t.out = scratch.data_ptr()
+    if res is not None:
+        t.residual = res.data_ptr()
+        t.ldr = res.stride(0)
+    L = lib()
+    cur = torch.cuda.current_stream()
+    side = torch.cuda.Stream()
+    results = {}
+    n_rep = 6
+    for pair in (1, 2):
+        for tn in (256, 160, 128, 64, 32):
+            t.tile_n, t.cta_pair = tn, pair
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                if L.geo4d_tap_gemm(C.byref(t), C.c_void_p(side.cuda_stream)) != 0:
+                    continue   # configuration not legal for this shape
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=side):
+                        for _ in range(n_rep):
+                            check(L.geo4d_tap_gemm(C.byref(t), C.c_void_p(side.cuda_stream)), "autotune")
+                    g.replay()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    best = None
+                    for _ in range(3):
+                        e0.record(side)
+                        g.replay()
+                        e1.record(side)
+                        e1.synchronize()
+                        us = e0.elapsed_time(e1) * 1e3 / n_rep
+                        best = us if best is None else min(best, us)
+                    results[(tn, pair)] = best
+                    del g
+                except Exception:   # a configuration that cannot be captured is simply not a candidate
+                    continue
+    cur.wait_stream(side)
+    if not results:
+        _TUNED[key] = (0, 0)
+        return (0, 0)
+    cfg = min(results, key=results.get)
+    _TUNED[key] = cfg
+    _TUNE_LOG.append((key, cfg, results))
+    if os.environ.get("GEO4D_AUTOTUNE_VERBOSE") == "1":
+        print(f"[geo4d autotune] {key} -> tile_n={cfg[0]} {'pair' if cfg[1] == 2 else 'single'} "
+              f"{results[cfg]:.1f} us  (all: {dict((k, round(v, 1)) for k, v in sorted(results.items()))})", flush=True)
+    return cfg
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,

@@ -32,7 +32,7 @@ extern "C" {
 
 typedef void* g4_stream_t; /* cudaStream_t */
 
-#define GEO4D_ABI_VERSION 1
+#define GEO4D_ABI_VERSION 2
 
 int geo4d_abi_version(void);
 const char* geo4d_last_error(void);
@@ -94,6 +94,11 @@ typedef struct {
   int act;
   const void* residual;      /* bf16, same row indexing with ldr, added last; may alias out */
   int64_t ldr;
+  /* Tile overrides (ABI v2).  0 = let the library's cost model decide.  The result does not depend on them
+   * (every output element sees the same k-step sequence); they exist so that a host can time the legal
+   * configurations of a shape once and pin the fastest (geo4d_b200/ops.py: autotune). */
+  int32_t tile_n;            /* 0 | 32 | 64 | 128 | 160 | 256 output columns per tile */
+  int32_t cta_pair;          /* 0 auto | 1 single CTA (cta_group::1) | 2 CTA pair (cta_group::2, 256-row tiles) */
 } g4_gemm_desc;
 
 int geo4d_tap_gemm(const g4_gemm_desc* d, g4_stream_t stream);
@@ -123,6 +128,8 @@ int geo4d_temporal_attention(const void* q, const void* k, const void* v, int64_
  * the statistics pass: its first 16 KiB must be ZERO before the first call (allocate it zero-filled once);
  * every call leaves them zero again, so one buffer serves any number of calls on a stream.  num_stats <= 4096. */
 size_t geo4d_groupnorm_workspace_bytes(int num_stats, int rows_per_stat, int C);
+/* Debug aid: non-zero keeps statistics and apply as two launches instead of one cooperative launch. */
+void geo4d_debug_groupnorm_two_kernels(int on);
 int geo4d_groupnorm_silu(const void* x, int64_t ldx, void* y, int64_t ldy, int num_stats, int rows_per_stat,
                          int C, const float* gamma, const float* beta, float eps, int apply_silu,
                          void* workspace, size_t workspace_bytes, g4_stream_t stream);

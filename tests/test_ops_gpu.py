@@ -16,9 +16,10 @@ def _rel(a, b):
 
 
 @pytest.fixture(params=["single", "pair", "single-direct", "pair-direct"])
-def gemm_mode(request, cuda_device):
+def gemm_mode(request, cuda_device, monkeypatch):
     from geo4d_b200 import ops
     lib = ops.lib()
+    monkeypatch.setattr(ops, "_AUTOTUNE", False)     # the mode under test must not be overridden by the tuner
     lib.geo4d_debug_gemm_pair_mode(1 if request.param.startswith("pair") else 0)
     lib.geo4d_debug_gemm_direct_store(1 if request.param.endswith("direct") else 0)
     yield request.param
@@ -128,6 +129,43 @@ def test_bmm(gemm_mode):
     out = ops.bmm_nt(a, b, alpha=0.125, out_dtype=torch.float32)
     torch.cuda.synchronize()
     assert _rel(out, 0.125 * torch.einsum("bmk,bnk->bmn", a.float(), b.float())) < 1e-5
+
+
+def test_every_tile_configuration_gives_identical_bits(cuda_device, monkeypatch):
+    """tile_n / cta_pair only change the schedule: each output element sees the same k-step sequence, so all
+    legal configurations -- and therefore whatever the autotuner pins -- produce bit-identical results."""
+    from geo4d_b200 import ops
+    monkeypatch.setattr(ops, "_AUTOTUNE", False)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    M, K, n = 128 * 9 + 40, 320, 640
+    x = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(n, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    b = torch.randn(n, device="cuda", generator=g)
+    res = torch.randn(M, n, device="cuda", generator=g).bfloat16()
+    base = ops.linear(x, w, b, residual=res)
+    for pair in (1, 2):
+        for tn in (32, 64, 128, 160, 256):
+            monkeypatch.setattr(ops, "_FORCE_TILE", (tn, pair))
+            out = ops.linear(x, w, b, residual=res)
+            torch.cuda.synchronize()
+            assert torch.equal(out, base), (tn, pair)
+    monkeypatch.setattr(ops, "_FORCE_TILE", None)
+
+
+def test_autotune_pins_a_configuration(cuda_device, monkeypatch):
+    from geo4d_b200 import ops
+    monkeypatch.setattr(ops, "_AUTOTUNE", True)
+    g = torch.Generator(device="cuda").manual_seed(12)
+    x = torch.randn(4096, 640, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(640, 640, device="cuda", generator=g) / 25).bfloat16()
+    n0 = len(ops.tuned_configs())
+    a = ops.linear(x, w)
+    b = ops.linear(x, w)
+    assert len(ops.tuned_configs()) == n0 + 1            # tuned once, reused afterwards
+    key, cfg, timings = ops.tuned_configs()[-1]
+    assert cfg in timings and timings[cfg] == min(timings.values())
+    assert torch.equal(a, b)
+    assert _rel(a, x.float() @ w.float().t()) < BF16_TOL
 
 
 def test_bad_arguments_raise(cuda_device):
