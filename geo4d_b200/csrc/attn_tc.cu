@@ -193,11 +193,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         float p[32];
         if (kv_valid >= (c + 1) * 32) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) p[i] = exp2f(fmaf(__uint_as_float(v[i]), sl2, -mb));
+          for (int i = 0; i < 32; ++i) p[i] = ex2_ftz(fmaf(__uint_as_float(v[i]), sl2, -mb));
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            p[i] = (c * 32 + i < kv_valid) ? exp2f(fmaf(__uint_as_float(v[i]), sl2, -mb)) : 0.f;
+            p[i] = (c * 32 + i < kv_valid) ? ex2_ftz(fmaf(__uint_as_float(v[i]), sl2, -mb)) : 0.f;
         }
         uint8_t* prow = sP + (c >> 1) * 16384 + r * 128;
 #pragma unroll
@@ -207,12 +207,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           w.y = pack_bf16x2(p[8 * qq + 2], p[8 * qq + 3]);
           w.z = pack_bf16x2(p[8 * qq + 4], p[8 * qq + 5]);
           w.w = pack_bf16x2(p[8 * qq + 6], p[8 * qq + 7]);
-          // row sum over the bf16-rounded probabilities (what the PV MMA actually sums)
-          float2 f;
-          f = unpack_bf16x2(w.x); rs += f.x + f.y;
-          f = unpack_bf16x2(w.y); rs += f.x + f.y;
-          f = unpack_bf16x2(w.z); rs += f.x + f.y;
-          f = unpack_bf16x2(w.w); rs += f.x + f.y;
+          // row sum in fp32 over the unrounded probabilities (as the flash kernels the reference calls do)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rs += p[8 * qq + i];
           const int chunk = ((c & 1) * 4 + qq) ^ (r & 7);
           *reinterpret_cast<uint4*>(prow + chunk * 16) = w;
         }

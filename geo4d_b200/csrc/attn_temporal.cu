@@ -95,8 +95,8 @@ temporal_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* _
       m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
       m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1));
       m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
-      s0[0] = exp2f(x0 - m_lo); s0[1] = exp2f(x1 - m_lo); s1[0] = exp2f(x2 - m_lo); s1[1] = exp2f(x3 - m_lo);
-      s0[2] = exp2f(y0 - m_hi); s0[3] = exp2f(y1 - m_hi); s1[2] = exp2f(y2 - m_hi); s1[3] = exp2f(y3 - m_hi);
+      s0[0] = ex2_ftz(x0 - m_lo); s0[1] = ex2_ftz(x1 - m_lo); s1[0] = ex2_ftz(x2 - m_lo); s1[1] = ex2_ftz(x3 - m_lo);
+      s0[2] = ex2_ftz(y0 - m_hi); s0[3] = ex2_ftz(y1 - m_hi); s1[2] = ex2_ftz(y2 - m_hi); s1[3] = ex2_ftz(y3 - m_hi);
       l_lo = s0[0] + s0[1] + s1[0] + s1[1];
       l_hi = s0[2] + s0[3] + s1[2] + s1[3];
       l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1);

@@ -110,11 +110,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, p;\n\t}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
+      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)   // suspend-time hint (ns): a waiting warp sleeps in hardware
+      : "memory");                                      // instead of burning issue slots its SM sub-partition shares
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
@@ -371,6 +371,11 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
+}
+__device__ __forceinline__ float ex2_ftz(float x) {   // one MUFU op; exp2f() adds a denormal-range fix-up (3 instr)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 // exact-erf GELU x * Phi(x), Phi(x) = 0.5 * erfc(-x / sqrt 2), with erfc(z >= 0) = poly(t) * exp(-z^2),
