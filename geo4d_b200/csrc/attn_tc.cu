@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(192, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnArgs args) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bars[12];
+  __shared__ uint64_t bars[13];
   __shared__ uint32_t tmem_slot;
   uint8_t* sQ = smem;
   uint8_t* sK = smem + AT_Q_BYTES;                    // [2]
@@ -52,6 +52,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* s_full = &bars[9];
   uint64_t* p_ready = &bars[10];
   uint64_t* pv_done = &bars[11];
+  uint64_t* s_free = &bars[12];  // the softmax warps hold S_j in registers: QK_{j+1} may overwrite it
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x % args.n_qtiles;
@@ -75,6 +76,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(s_full, 1);
     mbar_init(p_ready, 128);
     mbar_init(pv_done, 1);
+    mbar_init(s_free, 128);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -110,13 +112,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);  // B (= V) is MN-major
       const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
       mbar_wait(q_full, 0);
-      for (int j = 0; j < nkv; ++j) {
+      auto issue_qk = [&](int j) {
         const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
         const uint32_t aK = smem_u32(sK + st * AT_KV_BYTES);
-        const uint32_t aV = smem_u32(sV + st * AT_KV_BYTES);
-        // S_j = Q K_j^T  (S is free: the softmax warps finished reading S_{j-1} before p_ready(j-1))
-        mbar_wait(&k_full[st], ph);
+        mbar_wait(&k_full[st], (j >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
@@ -124,6 +123,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                   kk != 0);
         umma_commit(&k_empty[st]);
         umma_commit(s_full);
+      };
+      issue_qk(0);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        const uint32_t aV = smem_u32(sV + st * AT_KV_BYTES);
+        // S_{j+1} = Q K_{j+1}^T as soon as the softmax warps have S_j in registers: it runs under softmax(j)
+        if (j + 1 < nkv) {
+          mbar_wait(s_free, j & 1);
+          issue_qk(j + 1);
+        }
         // O += P_j V_j
         mbar_wait(&v_full[st], ph);
         mbar_wait(p_ready, j & 1);
@@ -149,24 +159,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int kv_valid = min(128, args.Lk - j * 128);  // keys of this tile that exist
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // pass 1: row max
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tS + lane_off + c * 32, v);
-        tmem_ld_wait();
-        if (kv_valid >= (c + 1) * 32) {
+      // the whole score row goes to registers with ONE TMEM round trip; S is then free for QK_{j+1}
+      uint32_t sv[4][32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        } else {
+      for (int c = 0; c < 4; ++c) tmem_ld32(tS + lane_off + c * 32, sv[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_free);
+      float mx = -INFINITY;
+      if (kv_valid == 128) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[c][i]));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-        }
+            if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(sv[c][i]));
       }
       const float m_new = fmaxf(m, mx);
-      const float alpha = (m == -INFINITY) ? 0.f : exp2f((m - m_new) * sl2);
+      const float alpha = (m == -INFINITY) ? 0.f : ex2_ftz((m - m_new) * sl2);
       const float mb = m_new * sl2;
       // the previous PV must have retired before O is rescaled / P is overwritten
       mbar_wait(pv_done, (j & 1) ^ 1);
@@ -183,33 +197,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         tmem_st_wait();
       }
-      // pass 2: p = exp2(s*sl2 - m*sl2), row sum, bf16 P tile (K-major, 128B swizzle) to smem
+      // p = exp2(s*sl2 - m*sl2), row sum, bf16 P tile (K-major, 128B swizzle) to smem
       float rs = 0.f;
-#pragma unroll 1
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tS + lane_off + c * 32, v);
-        tmem_ld_wait();
-        float p[32];
-        if (kv_valid >= (c + 1) * 32) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) p[i] = ex2_ftz(fmaf(__uint_as_float(v[i]), sl2, -mb));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            p[i] = (c * 32 + i < kv_valid) ? ex2_ftz(fmaf(__uint_as_float(v[i]), sl2, -mb)) : 0.f;
-        }
         uint8_t* prow = sP + (c >> 1) * 16384 + r * 128;
 #pragma unroll
         for (int qq = 0; qq < 4; ++qq) {
-          uint4 w;
-          w.x = pack_bf16x2(p[8 * qq + 0], p[8 * qq + 1]);
-          w.y = pack_bf16x2(p[8 * qq + 2], p[8 * qq + 3]);
-          w.z = pack_bf16x2(p[8 * qq + 4], p[8 * qq + 5]);
-          w.w = pack_bf16x2(p[8 * qq + 6], p[8 * qq + 7]);
-          // row sum in fp32 over the unrounded probabilities (as the flash kernels the reference calls do)
+          float p[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) rs += p[8 * qq + i];
+          for (int i = 0; i < 8; ++i) {
+            const int col = c * 32 + qq * 8 + i;
+            const float e = ex2_ftz(fmaf(__uint_as_float(sv[c][qq * 8 + i]), sl2, -mb));
+            p[i] = (kv_valid == 128 || col < kv_valid) ? e : 0.f;
+            rs += p[i];   // fp32 row sum over the unrounded probabilities (as the flash kernels the reference calls do)
+          }
+          uint4 w;
+          w.x = pack_bf16x2(p[0], p[1]);
+          w.y = pack_bf16x2(p[2], p[3]);
+          w.z = pack_bf16x2(p[4], p[5]);
+          w.w = pack_bf16x2(p[6], p[7]);
           const int chunk = ((c & 1) * 4 + qq) ^ (r & 7);
           *reinterpret_cast<uint4*>(prow + chunk * 16) = w;
         }
