@@ -117,7 +117,8 @@ class LightPointCloudGroupOptimizer(nn.Module):
                  flow_loss_fn="smooth_l1", flow_loss_weight=0.0, depth_regularize_weight=0.0, num_total_iter=300,
                  temporal_smoothing_weight=0, translation_weight=0.1, flow_loss_start_epoch=0.15, flow_loss_thre=50,
                  sintel_ckpt=False, use_self_mask=False, pxl_thre=50, sam2_mask_refine=True, motion_mask_thre=0.35,
-                 conf_optimize=False, depth_traj_start_iter=150, use_cuda_graph=True, lad_max_iters=5000):
+                 conf_optimize=False, depth_traj_start_iter=150, use_cuda_graph=True, lad_max_iters=5000,
+                 shard_sub_alignments=True):
         super().__init__()
         if dist != "l1" or conf not in ("id", "none") or not shared_focal or not conf_optimize or opt_raydir \
                 or optimize_pp or allow_pw_adaptors or flow_loss_weight != 0.0 or depth_regularize_weight != 0.0:
@@ -146,6 +147,7 @@ class LightPointCloudGroupOptimizer(nn.Module):
         self.has_im_poses = True
         self.use_cuda_graph = use_cuda_graph and os.environ.get("GEO4D_ALIGN_EAGER", "0") != "1"
         self.lad_max_iters = lad_max_iters
+        self.shard_sub_alignments = shard_sub_alignments  # split per-window LAD fits over torch.distributed ranks
         self._profile = None
         dev = p0.device
         G, gs, N, HW = self.n_groups, self.group_size, self.n_imgs, self.HW
@@ -431,54 +433,94 @@ class LightPointCloudGroupOptimizer(nn.Module):
     # ------------------------------------------------------------------ iteration-150 sub-alignments
     @torch.no_grad()
     def _set_st_depth(self):
-        """optimizer_group.py:333-372 with the LAD fit of depth_eval.py:112-145 on the GPU."""
+        """optimizer_group.py:333-372 with the LAD fit of depth_eval.py:112-145 on the GPU.  The per-window fits are
+        independent, so under torch.distributed (one process per GPU, replicated alignment) each rank fits the
+        windows g with g % world == rank and the (s, t, delta<1.25) triples are all-gathered: every rank ends up
+        with bit-identical values and the stage costs one window's fit instead of G."""
         G, n = self.n_groups, self.group_size * self.HW
         dev = self.device
-        y = (1.0 / (self.im_depthmaps.exp() + 1e-6))[self._e_all].reshape(G, n).contiguous()
-        x = self._stacked_depthmap_all.reshape(G, n)
-        w = self._weight_all.reshape(G, n)
-        s_init = torch.median(y, dim=1).values / torch.median(x, dim=1).values
+        y_all = (1.0 / (self.im_depthmaps.exp() + 1e-6))[self._e_all].reshape(G, n)
+        x_all = self._stacked_depthmap_all.reshape(G, n)
+        w_all = self._weight_all.reshape(G, n)
 
-        def fit(lr, iters):
-            state = torch.zeros(G, 9, device=dev)
-            state[:, 0] = s_init
-            acc = torch.zeros(G * 4, device=dev, dtype=torch.float64)
-            chunk = 250
-            graph = None
-            done_iters = 0
-            if self.use_cuda_graph and iters >= 2 * chunk:
-                ops.lad_step(x, y, n, G, state, acc, lr)  # warm-up (real iteration 0)
-                done_iters = 1
-                torch.cuda.synchronize()
-                graph = torch.cuda.CUDAGraph()
-                side = torch.cuda.Stream()
-                side.wait_stream(torch.cuda.current_stream())
-                n0 = ops.raw_launch_count()
-                with torch.cuda.stream(side), torch.cuda.graph(graph, stream=side):
-                    for _ in range(chunk):
-                        ops.lad_step(x, y, n, G, state, acc, lr)
-                torch.cuda.current_stream().wait_stream(side)
-                nk = ops.raw_launch_count() - n0
-                ops.note_replay(nk, -1)
-                while done_iters + chunk <= iters:
-                    graph.replay()
-                    ops.note_replay(nk)
-                    done_iters += chunk
-            for _ in range(iters - done_iters):
-                ops.lad_step(x, y, n, G, state, acc, lr)
-            d = ops.delta125(x, y, w, n, G, state, 9).cpu().numpy()
-            d1 = np.where(d[:, 1] > 0, d[:, 0] / np.maximum(d[:, 1], 1), 0.0)
-            return state[:, :2].clone(), d1
+        def solve(sel):
+            k = len(sel)
+            idx = torch.tensor(sel, device=dev, dtype=torch.long)
+            x, y, w = x_all[idx].contiguous(), y_all[idx].contiguous(), w_all[idx].contiguous()
+            s_init = torch.median(y, dim=1).values / torch.median(x, dim=1).values
 
-        best_st, best_d1 = fit(1e-2, self.lad_max_iters)
-        retry = best_d1 < 0.8
-        if retry.any():
-            for lr in (1e-4, 1e-3):
-                st, d1 = fit(lr, min(3000, self.lad_max_iters))
-                better = retry & (d1 > best_d1)
-                bt = torch.tensor(better, device=dev)
-                best_st = torch.where(bt[:, None], st, best_st)
-                best_d1 = np.where(better, d1, best_d1)
+            def fit(lr, iters):
+                state = torch.zeros(k, 9, device=dev)
+                state[:, 0] = s_init
+                acc = torch.zeros(k * 4, device=dev, dtype=torch.float64)
+                if self.use_cuda_graph and os.environ.get("GEO4D_LAD_STEPWISE", "0") != "1":
+                    # one cooperative launch for the whole fit (grid barrier per iteration, data held in smem)
+                    ops.lad_fit(x, y, n, k, state, acc, lr, iters)
+                    d = ops.delta125(x, y, w, n, k, state, 9).cpu().numpy()
+                    d1 = np.where(d[:, 1] > 0, d[:, 0] / np.maximum(d[:, 1], 1), 0.0)
+                    return state[:, :2].clone(), d1
+                chunk = 250
+                graph = None
+                done_iters = 0
+                if self.use_cuda_graph and iters >= 2 * chunk:
+                    ops.lad_step(x, y, n, k, state, acc, lr)  # warm-up (real iteration 0)
+                    done_iters = 1
+                    torch.cuda.synchronize()
+                    graph = torch.cuda.CUDAGraph()
+                    side = torch.cuda.Stream()
+                    side.wait_stream(torch.cuda.current_stream())
+                    n0 = ops.raw_launch_count()
+                    with torch.cuda.stream(side), torch.cuda.graph(graph, stream=side):
+                        for _ in range(chunk):
+                            ops.lad_step(x, y, n, k, state, acc, lr)
+                    torch.cuda.current_stream().wait_stream(side)
+                    nk = ops.raw_launch_count() - n0
+                    ops.note_replay(nk, -1)
+                    while done_iters + chunk <= iters:
+                        graph.replay()
+                        ops.note_replay(nk)
+                        done_iters += chunk
+                        # the kernel freezes a window once |delta loss| < tol (depth_eval.py:139-141 breaks there);
+                        # one flag read per 250 iterations stops launching no-op kernels when every window is done
+                        if bool((state[:, 8] != 0).all()):
+                            done_iters = iters
+                            break
+                for _ in range(iters - done_iters):
+                    ops.lad_step(x, y, n, k, state, acc, lr)
+                d = ops.delta125(x, y, w, n, k, state, 9).cpu().numpy()
+                d1 = np.where(d[:, 1] > 0, d[:, 0] / np.maximum(d[:, 1], 1), 0.0)
+                return state[:, :2].clone(), d1
+
+            best_st, best_d1 = fit(1e-2, self.lad_max_iters)
+            retry = best_d1 < 0.8
+            if retry.any():
+                for lr in (1e-4, 1e-3):
+                    st, d1 = fit(lr, min(3000, self.lad_max_iters))
+                    better = retry & (d1 > best_d1)
+                    bt = torch.tensor(better, device=dev)
+                    best_st = torch.where(bt[:, None], st, best_st)
+                    best_d1 = np.where(better, d1, best_d1)
+            return best_st, best_d1
+
+        world, rank = 1, 0
+        if self.shard_sub_alignments and torch.distributed.is_available() and torch.distributed.is_initialized():
+            world, rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
+        if world > 1 and G > 1:
+            per = -(-G // world)
+            mine = [g for g in range(G) if g % world == rank]
+            rec = torch.zeros(per, 3, device=dev, dtype=torch.float64)
+            if mine:
+                st, d1 = solve(mine)
+                rec[:len(mine), :2] = st.double()
+                rec[:len(mine), 2] = torch.as_tensor(d1, device=dev, dtype=torch.float64)
+            allrec = torch.empty(world * per, 3, device=dev, dtype=torch.float64)
+            torch.distributed.all_gather_into_tensor(allrec, rec)
+            allrec = allrec.view(world, per, 3)
+            order = [(g % world, g // world) for g in range(G)]
+            full = torch.stack([allrec[r, j] for r, j in order])
+            best_st, best_d1 = full[:, :2].float(), full[:, 2].cpu().numpy()
+        else:
+            best_st, best_d1 = solve(list(range(G)))
         self.s_depth.data[:, 0] = best_st[:, 0]
         self.t_depth.data[:, 0] = best_st[:, 1]
         return [int(i) for i in np.nonzero(best_d1 < 0.3)[0]]

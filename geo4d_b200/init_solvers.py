@@ -138,12 +138,22 @@ def _sqp_refine(r: np.ndarray, Omega: np.ndarray, max_iter: int = 15, tol: float
         J[3, 0:3], J[3, 3:6] = r2, r1
         J[4, 0:3], J[4, 6:9] = r3, r1
         J[5, 3:6], J[5, 6:9] = r3, r2
-        U, S, Vt = np.linalg.svd(J)
-        d_rs = Vt[:6].T @ ((U.T @ (-g)) / S)      # min-norm solution of J d = -g
-        N = Vt[6:].T                               # null space of J (9 x 3)
-        A = N.T @ Omega @ N
-        y = -np.linalg.solve(A, N.T @ Omega @ (r + d_rs))
-        d = d_rs + N @ y
+        # one SQP step = the equality-constrained QP  min (r+d)^T Omega (r+d)  s.t.  J d = -g, solved through its
+        # 15x15 KKT system (same step as the null-space form: min-norm solution of J d = -g plus the minimiser
+        # over null(J), but one small LU instead of a 6x9 SVD)
+        K = np.zeros((15, 15))
+        K[:9, :9] = Omega
+        K[:9, 9:] = J.T
+        K[9:, :9] = J
+        rhs = np.concatenate([-(Omega @ r), -g])
+        try:
+            d = np.linalg.solve(K, rhs)[:9]
+        except np.linalg.LinAlgError:
+            U, S, Vt = np.linalg.svd(J)
+            d_rs = Vt[:6].T @ ((U.T @ (-g)) / S)
+            N = Vt[6:].T
+            y = -np.linalg.solve(N.T @ Omega @ N, N.T @ Omega @ (r + d_rs))
+            d = d_rs + N @ y
         r = r + d
         if d @ d < tol:
             break
@@ -196,6 +206,113 @@ def sqpnp_from_moments(mom: np.ndarray, f: float):
     return best[1], best[2]
 
 
+def _nearest_rotation_batch(E: np.ndarray) -> np.ndarray:
+    """E [B, 9] -> nearest rotations [B, 9] (batched _nearest_rotation)."""
+    U, _, Vt = np.linalg.svd(E.reshape(-1, 3, 3))
+    R = U @ Vt
+    neg = np.linalg.det(R) < 0
+    if neg.any():
+        D = np.diag([1.0, 1.0, -1.0])
+        R[neg] = U[neg] @ D @ Vt[neg]
+    return R.reshape(-1, 9)
+
+
+def _sqp_refine_batch(r: np.ndarray, Omega: np.ndarray, max_iter: int = 15, tol: float = 1e-10) -> np.ndarray:
+    """_sqp_refine for B problems at once: r [B, 9], Omega [B, 9, 9] (one batched 15x15 KKT solve per iteration)."""
+    r = r.copy()
+    B = r.shape[0]
+    active = np.ones(B, dtype=bool)
+    for _ in range(max_iter):
+        r1, r2, r3 = r[:, 0:3], r[:, 3:6], r[:, 6:9]
+        g = np.stack([(r1 * r1).sum(1) - 1, (r2 * r2).sum(1) - 1, (r3 * r3).sum(1) - 1, (r1 * r2).sum(1),
+                      (r1 * r3).sum(1), (r2 * r3).sum(1)], 1)
+        J = np.zeros((B, 6, 9))
+        J[:, 0, 0:3] = 2 * r1
+        J[:, 1, 3:6] = 2 * r2
+        J[:, 2, 6:9] = 2 * r3
+        J[:, 3, 0:3], J[:, 3, 3:6] = r2, r1
+        J[:, 4, 0:3], J[:, 4, 6:9] = r3, r1
+        J[:, 5, 3:6], J[:, 5, 6:9] = r3, r2
+        K = np.zeros((B, 15, 15))
+        K[:, :9, :9] = Omega
+        K[:, :9, 9:] = J.transpose(0, 2, 1)
+        K[:, 9:, :9] = J
+        rhs = np.concatenate([-np.einsum("bij,bj->bi", Omega, r), -g], 1)
+        d = np.linalg.solve(K, rhs[..., None])[:, :9, 0]
+        d[~active] = 0.0
+        r = r + d
+        active &= (d * d).sum(1) >= tol
+        if not active.any():
+            break
+    return r
+
+
+def sqpnp_from_moments_batch(moms: np.ndarray, focals) -> list:
+    """sqpnp_from_moments for B (moments, focal) pairs with the linear algebra batched.  Cases that need more than
+    the smallest eigenvector, or that hit a singular system, fall back to the scalar routine."""
+    B = len(focals)
+    out = [None] * B
+    moms = np.asarray(moms, dtype=np.float64).reshape(B, -1)
+    f = np.asarray(focals, dtype=np.float64)
+    good = (moms[:, 0] >= 4) & np.isfinite(f) & (f > 0)
+    idx = np.nonzero(good)[0]
+    if len(idx) == 0:
+        return out
+    try:
+        m = moms[idx]
+        n = m[:, 0]
+        s1, s2 = 1.0 / f[idx], 1.0 / (f[idx] * f[idx])
+        k = len(idx)
+        SQ = np.zeros((k, 3, 3))
+        SQ[:, 0, 0] = n; SQ[:, 1, 1] = n
+        SQ[:, 0, 2] = SQ[:, 2, 0] = -s1 * m[:, 1]
+        SQ[:, 1, 2] = SQ[:, 2, 1] = -s1 * m[:, 2]
+        SQ[:, 2, 2] = s2 * m[:, 3]
+        Sm, Sxm, Sym, Srm = m[:, 4:7], s1[:, None] * m[:, 7:10], s1[:, None] * m[:, 10:13], s2[:, None] * m[:, 13:16]
+        QA = np.zeros((k, 3, 9))
+        QA[:, 0, 0:3], QA[:, 0, 6:9] = Sm, -Sxm
+        QA[:, 1, 3:6], QA[:, 1, 6:9] = Sm, -Sym
+        QA[:, 2, 0:3], QA[:, 2, 3:6], QA[:, 2, 6:9] = -Sxm, -Sym, Srm
+
+        def sym(v):
+            M = np.empty((k, 3, 3))
+            M[:, 0, 0], M[:, 0, 1], M[:, 0, 2] = v[:, 0], v[:, 1], v[:, 2]
+            M[:, 1, 0], M[:, 1, 1], M[:, 1, 2] = v[:, 1], v[:, 3], v[:, 4]
+            M[:, 2, 0], M[:, 2, 1], M[:, 2, 2] = v[:, 2], v[:, 4], v[:, 5]
+            return M
+        Mm, Mx, My, Mr = sym(m[:, 16:22]), s1[:, None, None] * sym(m[:, 22:28]), s1[:, None, None] * sym(m[:, 28:34]), \
+            s2[:, None, None] * sym(m[:, 34:40])
+        AQA = np.zeros((k, 9, 9))
+        AQA[:, 0:3, 0:3] = Mm; AQA[:, 3:6, 3:6] = Mm; AQA[:, 6:9, 6:9] = Mr
+        AQA[:, 0:3, 6:9] = -Mx; AQA[:, 6:9, 0:3] = -Mx
+        AQA[:, 3:6, 6:9] = -My; AQA[:, 6:9, 3:6] = -My
+        P = -np.linalg.solve(SQ, QA)
+        Omega = AQA + QA.transpose(0, 2, 1) @ P
+        Omega = 0.5 * (Omega + Omega.transpose(0, 2, 1))
+        w, V = np.linalg.eigh(Omega)
+        e0 = V[:, :, 0]
+        mean_pt = Sm / n[:, None]
+        start = np.concatenate([np.sqrt(3.0) * e0, -np.sqrt(3.0) * e0], 0)            # both signs
+        Om2 = np.concatenate([Omega, Omega], 0)
+        r = _nearest_rotation_batch(_sqp_refine_batch(_nearest_rotation_batch(start), Om2))
+        t = np.einsum("bij,bj->bi", np.concatenate([P, P], 0), r)
+        cheir = (r[:, 6:9] * np.concatenate([mean_pt, mean_pt], 0)).sum(1) + t[:, 2] > 0
+        err = np.einsum("bi,bij,bj->b", r, Om2, r)
+        for j, i in enumerate(idx):
+            best = None
+            for c in (j, j + k):
+                if cheir[c] and (best is None or err[c] < best[0]):
+                    best = (float(err[c]), r[c].reshape(3, 3), t[c])
+            if best is None or best[0] > 3 * w[j, 1]:
+                out[i] = sqpnp_from_moments(moms[i], float(f[i]))   # rare: look at more eigenvectors
+            else:
+                out[i] = (best[1], best[2])
+    except np.linalg.LinAlgError:
+        for i in idx:
+            out[i] = sqpnp_from_moments(moms[i], float(f[i]))
+    return out
+
+
 def gpu_fast_pnp_frames(ops, pts: "torch.Tensor", conf: "torch.Tensor", H: int, W: int, first_focal_of, im_focals,
                         im_poses, frame_ids, niter_PnP: int = 10, thr_px: float = 5.0):
     """fast_pnp (init_im_poses.py:824-865) for the frames of one window with the reductions on the GPU:
@@ -215,7 +332,7 @@ def gpu_fast_pnp_frames(ops, pts: "torch.Tensor", conf: "torch.Tensor", H: int, 
             lo, hi = -0.03 * S + focal, 0.03 * S + focal
             tentative = [focal] + ([float(x) for x in np.geomspace(lo, hi, 2)] if lo > 0 else [])
         tentative = [float(f) for f in tentative if np.isfinite(f) and f > 0]
-        sols = [sqpnp_from_moments(mom_all[k], f) for f in tentative]
+        sols = sqpnp_from_moments_batch(np.repeat(mom_all[k][None], len(tentative), 0), tentative)
         ok = [i for i, s in enumerate(sols) if s is not None]
         if ok:
             gate = np.zeros((1, len(ok), 13), dtype=np.float32)
@@ -227,14 +344,14 @@ def gpu_fast_pnp_frames(ops, pts: "torch.Tensor", conf: "torch.Tensor", H: int, 
             g = torch.from_numpy(gate).to(pts.device)
             mom_in = ops.pnp_moments(pts[k:k + 1], conf[k:k + 1], 1, HW, W, cx, cy, gate=g, ncand=len(ok),
                                      thr_px=thr_px).cpu().numpy()[0]
+            refit = sqpnp_from_moments_batch(mom_in[:len(ok)], [tentative[i] for i in ok])
             best = (0, None, None)
             for j, i in enumerate(ok):
                 ninl = int(round(mom_in[j, 40]))
                 if ninl < 4 or ninl <= best[0]:
                     continue
-                sol = sqpnp_from_moments(mom_in[j], tentative[i])
-                if sol is not None:
-                    best = (ninl, sol, tentative[i])
+                if refit[j] is not None:
+                    best = (ninl, refit[j], tentative[i])
             if best[0]:
                 R, t = best[1]
                 w2c = np.eye(4)

@@ -416,6 +416,11 @@ def lad_step(x, y, n_per_group: int, G: int, state, acc, lr: float, tol: float =
                                C.c_float(tol), _s()), "geo4d_lad_step")
 
 
+def lad_fit(x, y, n_per_group: int, G: int, state, acc, lr: float, iters: int, tol: float = 1e-6):
+    check(lib().geo4d_lad_fit(_vp(x), _vp(y), C.c_int64(n_per_group), G, _vp(state), _vp(acc), C.c_float(lr),
+                              C.c_float(tol), int(iters), _s()), "geo4d_lad_fit")
+
+
 def delta125(x, y, w, n_per_group: int, G: int, st, st_stride: int) -> torch.Tensor:
     out = torch.empty((G, 2), device=x.device, dtype=torch.float64)
     check(lib().geo4d_delta125(_vp(x), _vp(y), _vp(w), C.c_int64(n_per_group), G, _vp(st), st_stride, _vp(out), _s()),

@@ -196,6 +196,10 @@ int geo4d_align_iter(float* logd, float* adam_m, float* adam_v, const float* pre
  * step, done}; acc = 4*G doubles of scratch (3 sums + an arrival ticket per window), zero before the first call. */
 int geo4d_lad_step(const float* x, const float* y, int64_t n_per_group, int G, float* state, double* acc, float lr,
                    float tol, g4_stream_t stream);
+/* The whole fit (up to `iters` iterations of geo4d_lad_step, same arithmetic and early exit) in one cooperative
+ * launch with a per-window grid barrier; needs G <= number of SMs.  acc as above (4*G doubles, zero on entry). */
+int geo4d_lad_fit(const float* x, const float* y, int64_t n_per_group, int G, float* state, double* acc, float lr,
+                  float tol, int iters, g4_stream_t stream);
 /* delta<1.25 accuracy of s*x+t vs y under (w>0.5 & x>0.05 & y>0) (depth_eval.py:296-317): out[g] = {ok, n}. */
 int geo4d_delta125(const float* x, const float* y, const float* w, int64_t n_per_group, int G, const float* st,
                    int st_stride, double* out, g4_stream_t stream);
