@@ -41,6 +41,15 @@ def peaks():
     return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback")
 
 
+def unet_step_traffic():
+    """DRAM bytes (read + write) of the roofline unit from the committed ncu pass, or None."""
+    p = os.path.join(REPO, "profiles", "r1_unet_step_traffic.json")
+    try:
+        return json.load(open(p))["dram_bytes"]
+    except Exception:
+        return None
+
+
 def kernel_rooflines(dev, pk):
     """Live per-kernel numbers for the dominant kernel (tap_gemm_kernel) on its heaviest U-Net shapes and for the
     attention kernel: each launch is timed GPU-bound (20 launches in a CUDA graph, CUDA events on the launching
@@ -54,7 +63,7 @@ def kernel_rooflines(dev, pk):
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=side):
+            with ops.capture_graph(g):
                 for _ in range(n):
                     fn()
             g.replay()
@@ -308,7 +317,7 @@ def main():
         ach = tflop / (unet_ms * 1e-3)
         roof = {"bound": "tensor", "kernel": "U-Net step (1 CUDA-graph launch; tap_gemm_kernel = 93% of its FLOPs)",
                 "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
-                "peak_source": pk["source"] + " (sustained: timed inside a long step)", "traffic": None,
+                "peak_source": pk["source"] + " (sustained: timed inside a long step)", "traffic": unet_step_traffic(),
                 "algorithmic_tflop_per_launch": tflop, "ms_per_launch": unet_ms}
         try:
             roof["kernels"] = kernel_rooflines(dev, pk)

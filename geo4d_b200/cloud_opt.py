@@ -470,7 +470,7 @@ class LightPointCloudGroupOptimizer(nn.Module):
                     side = torch.cuda.Stream()
                     side.wait_stream(torch.cuda.current_stream())
                     n0 = ops.raw_launch_count()
-                    with torch.cuda.stream(side), torch.cuda.graph(graph, stream=side):
+                    with torch.cuda.stream(side), ops.capture_graph(graph):
                         for _ in range(chunk):
                             ops.lad_step(x, y, n, k, state, acc, lr)
                     torch.cuda.current_stream().wait_stream(side)
@@ -664,7 +664,7 @@ class LightPointCloudGroupOptimizer(nn.Module):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         n0 = ops.raw_launch_count()
-        with torch.cuda.stream(side), torch.cuda.graph(graph, stream=side):
+        with torch.cuda.stream(side), ops.capture_graph(graph):
             self._iteration_fused(st)
         torch.cuda.current_stream().wait_stream(side)
         nk = ops.raw_launch_count() - n0
@@ -689,7 +689,7 @@ class LightPointCloudGroupOptimizer(nn.Module):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         n0 = ops.raw_launch_count()
-        with torch.cuda.stream(side), torch.cuda.graph(graph, stream=side):
+        with torch.cuda.stream(side), ops.capture_graph(graph):
             self._iteration(st, phase_b)
         torch.cuda.current_stream().wait_stream(side)
         nk = ops.raw_launch_count() - n0

@@ -27,6 +27,24 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class capture_graph:
+    """`with capture_graph(g): ...` records the launches of the block into the torch.cuda.CUDAGraph `g` on the
+    CURRENT stream (which must be a side stream).  Unlike `torch.cuda.graph` it does not run gc.collect() and
+    torch.cuda.empty_cache() first: those cost 50-1000 ms per capture once a 25 GB pipeline is resident and hand
+    every cached block back to the driver, and the alignment captures two small graphs per call."""
+
+    def __init__(self, graph: "torch.cuda.CUDAGraph"):
+        self.graph = graph
+
+    def __enter__(self):
+        self.graph.capture_begin()
+        return self.graph
+
+    def __exit__(self, exc_type, exc, tb):
+        self.graph.capture_end()
+        return False
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -138,7 +156,7 @@ def _autotune(d: GemmDesc, key, out: torch.Tensor, residual: Optional[torch.Tens
                     continue   # configuration not legal for this shape
                 try:
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, stream=side):
+                    with capture_graph(g):
                         for _ in range(n_rep):
                             check(L.geo4d_tap_gemm(C.byref(t), C.c_void_p(side.cuda_stream)), "autotune")
                     g.replay()

@@ -157,7 +157,7 @@ class DDIMSampler(object):
                 side.wait_stream(torch.cuda.current_stream())
                 n0 = ops.raw_launch_count()
                 with torch.cuda.stream(side):
-                    with torch.cuda.graph(g, stream=side):
+                    with ops.capture_graph(g):
                         one_step()
                 torch.cuda.current_stream().wait_stream(side)
                 st["graph"] = g
