@@ -3,6 +3,7 @@
 Usage under ncu:  ncu --set full --clock-control none --import-source on -k regex:'tap_gemm|attn_fwd|gn_|layernorm|temporal_attn|align_iter' \
                       -o gpurun_out/prof python tools/prof_kernels.py"""
 import os, sys
+os.environ.setdefault("GEO4D_AUTOTUNE", "0")   # under ncu every tuning launch would be profiled too
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 import torch
@@ -12,7 +13,7 @@ def main():
     dev = "cuda"
     torch.manual_seed(0)
     bf = lambda *s: torch.randn(*s, device=dev).bfloat16()
-    reps = int(os.environ.get("REPS", "2"))
+    reps = int(os.environ.get("REPS", "1"))
     M = 40960
     for _ in range(reps):
         # linears (level 0)
