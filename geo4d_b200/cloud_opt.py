@@ -506,18 +506,15 @@ class LightPointCloudGroupOptimizer(nn.Module):
         if self.shard_sub_alignments and torch.distributed.is_available() and torch.distributed.is_initialized():
             world, rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
         if world > 1 and G > 1:
+            from . import sharding
             per = -(-G // world)
-            mine = [g for g in range(G) if g % world == rank]
+            mine = sharding.windows_for_rank(G, rank, world)
             rec = torch.zeros(per, 3, device=dev, dtype=torch.float64)
             if mine:
                 st, d1 = solve(mine)
                 rec[:len(mine), :2] = st.double()
                 rec[:len(mine), 2] = torch.as_tensor(d1, device=dev, dtype=torch.float64)
-            allrec = torch.empty(world * per, 3, device=dev, dtype=torch.float64)
-            torch.distributed.all_gather_into_tensor(allrec, rec)
-            allrec = allrec.view(world, per, 3)
-            order = [(g % world, g // world) for g in range(G)]
-            full = torch.stack([allrec[r, j] for r, j in order])
+            full = sharding.gather_group_records(rec, G)
             best_st, best_d1 = full[:, :2].float(), full[:, 2].cpu().numpy()
         else:
             best_st, best_d1 = solve(list(range(G)))

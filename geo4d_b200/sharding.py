@@ -54,3 +54,19 @@ def gather_predictions(local: Dict[int, Dict[str, torch.Tensor]], n_windows: int
             off = (r * per_rank + slot) * rec
             out[w] = unpack_pred(recv[off:off + rec], T, H, W)
     return out
+
+
+def gather_group_records(local: torch.Tensor, n_groups: int, group=None) -> torch.Tensor:
+    """Per-window results computed round-robin over the ranks -> the full table on every rank.
+    local [ceil(n_groups / world), k]: row j holds this rank's j-th window (windows_for_rank order), unused rows
+    are ignored.  Returns [n_groups, k] in window order, identical on every rank (used for the LAD scale / shift
+    fits of the replicated global alignment)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    per = -(-n_groups // world)
+    assert local.shape[0] == per, (local.shape, per)
+    if world == 1:
+        return local[:n_groups].clone()
+    allrec = torch.empty((world * per,) + tuple(local.shape[1:]), device=local.device, dtype=local.dtype)
+    dist.all_gather_into_tensor(allrec, local.contiguous(), group=group)
+    allrec = allrec.view((world, per) + tuple(local.shape[1:]))
+    return torch.stack([allrec[g % world, g // world] for g in range(n_groups)])
