@@ -196,6 +196,10 @@ int geo4d_align_iter(float* logd, float* adam_m, float* adam_v, const float* pre
  * step, done}; acc = 4*G doubles of scratch (3 sums + an arrival ticket per window), zero before the first call. */
 int geo4d_lad_step(const float* x, const float* y, int64_t n_per_group, int G, float* state, double* acc, float lr,
                    float tol, g4_stream_t stream);
+/* HOST function (no CUDA): SQPnP from the 41 moments of one frame for focal f (the 9-unknown problem behind
+ * cv2.solvePnPRansac(flags=SOLVEPNP_SQPNP) in fast_pnp, init_im_poses.py:824-865).  Writes the world-to-camera
+ * rotation (row-major 3x3) and translation; returns 1 on success, 0 if there is no valid solution. */
+int geo4d_sqpnp_from_moments(const double* mom, double f, double* R_out, double* t_out);
 /* The whole fit (up to `iters` iterations of geo4d_lad_step, same arithmetic and early exit) in one cooperative
  * launch with a per-window grid barrier; needs G <= number of SMs.  acc as above (4*G doubles, zero on entry). */
 int geo4d_lad_fit(const float* x, const float* y, int64_t n_per_group, int G, float* state, double* acc, float lr,

@@ -94,3 +94,34 @@ def test_full_model_state_dict_layout(golden_dir):
               "sqrt_one_minus_alphas_cumprod", "posterior_variance", "posterior_mean_coef1"):
         assert b in keys
     assert m.scale_arr.shape[0] == 1400 and m.num_timesteps == 1000 and m.parameterization == "v"
+
+
+def test_native_sqpnp_matches_numpy():
+    """geo4d_sqpnp_from_moments (C++ host solver in the library) vs the NumPy statement of the same algorithm on
+    random poses / focals / noise levels / mask densities, including wrong tentative focals: same solution."""
+    import numpy as np
+    from scipy.spatial.transform import Rotation
+    from geo4d_b200 import init_solvers as isv
+    H, W = 48, 64
+    v, u = np.mgrid[:H, :W]
+    rng = np.random.default_rng(0)
+    compared = 0
+    for trial in range(60):
+        f = rng.uniform(40, 160)
+        z = rng.uniform(1.5, 8, (H, W))
+        pts = np.stack([(u - W / 2) * z / f, (v - H / 2) * z / f, z], -1) + rng.normal(0, rng.choice([0.0, 0.01, 0.1]), (H, W, 3))
+        Rw = Rotation.from_euler("xyz", rng.uniform(-1, 1, 3)).as_matrix()
+        tw = rng.uniform(-1, 1, 3)
+        world = (pts - tw) @ Rw                      # camera = Rw world + tw
+        mask = rng.random((H, W)) < rng.choice([1.0, 0.5, 0.05])
+        mom = isv.moments_numpy(world, mask, W / 2, H / 2)
+        ft = f * rng.choice([1.0, 0.97, 1.03, 1.3, 0.7])
+        a = isv.sqpnp_from_moments(mom, ft)
+        b = isv.sqpnp_from_moments_native(mom, ft)
+        assert (a is None) == (b is None)
+        if a is None:
+            continue
+        assert np.abs(a[0] - b[0]).max() < 1e-9 and np.abs(a[1] - b[1]).max() < 1e-9 * max(1.0, np.abs(a[1]).max())
+        compared += 1
+    assert compared > 40
+    assert isv.sqpnp_from_moments_native(np.zeros(41), 100.0) is None      # fewer than 4 points

@@ -65,7 +65,7 @@ def _worker_groups(rank, world, port, n_groups, ret):
 
 def test_gather_group_records_world2():
     """the per-window LAD results of the replicated alignment: fitted round-robin, identical table everywhere"""
-    for n_groups, port in ((2, 29621), (5, 29622), (1, 29623)):
+    for n_groups, port in ((2, 29621), (5, 29622)):
         with mp.Manager() as m:
             ret = m.dict()
             mp.spawn(_worker_groups, args=(2, port, n_groups, ret), nprocs=2, join=True)
