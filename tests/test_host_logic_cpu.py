@@ -125,3 +125,31 @@ def test_native_sqpnp_matches_numpy():
         compared += 1
     assert compared > 40
     assert isv.sqpnp_from_moments_native(np.zeros(41), 100.0) is None      # fewer than 4 points
+
+
+def test_native_sqpnp_matches_cv2_sqpnp():
+    """Pin against the library the reference actually calls: cv2.solvePnP(flags=SOLVEPNP_SQPNP) on all points (the
+    model-fitting step inside solvePnPRansac, init_im_poses.py:845-848) vs geo4d_sqpnp_from_moments fed with the 41
+    moments of the same correspondences -- including slightly wrong tentative focals, as fast_pnp tries them."""
+    import cv2
+    import numpy as np
+    from scipy.spatial.transform import Rotation
+    from geo4d_b200 import init_solvers as isv
+    H, W = 48, 64
+    v, u = np.mgrid[:H, :W]
+    rng = np.random.default_rng(1)
+    for trial in range(12):
+        f = rng.uniform(40, 160)
+        z = rng.uniform(1.5, 8, (H, W))
+        pts = np.stack([(u - W / 2) * z / f, (v - H / 2) * z / f, z], -1) + rng.normal(0, 0.02, (H, W, 3))
+        Rw = Rotation.from_euler("xyz", rng.uniform(-1, 1, 3)).as_matrix()
+        tw = rng.uniform(-1, 1, 3)
+        world = (pts - tw) @ Rw
+        mask = np.ones((H, W), bool)
+        ft = f * rng.choice([1.0, 0.97, 1.03])
+        got = isv.sqpnp_from_moments_native(isv.moments_numpy(world, mask, W / 2, H / 2), ft)
+        K = np.float64([(ft, 0, W / 2), (0, ft, H / 2), (0, 0, 1)])
+        pix = np.stack([u, v], -1).astype(np.float64)
+        ok, rv, tv = cv2.solvePnP(world[mask].astype(np.float64), pix[mask], K, None, flags=cv2.SOLVEPNP_SQPNP)
+        assert ok and got is not None
+        assert np.abs(cv2.Rodrigues(rv)[0] - got[0]).max() < 1e-7 and np.abs(tv.ravel() - got[1]).max() < 1e-7
