@@ -151,7 +151,9 @@ def run_reference(args, rank, world):
     import torch
     from oracle import unet as ou, vae as ov
     H, W = args.height, args.width
-    cores = os.cpu_count() or 1
+    # threads actually used: the sample's operators are small (one frame at 128x256); on the 128-thread GPU hosts an
+    # OpenMP team of 128 spends its time in fork/join (measured: ~15 busy cores, > 100 s per sample), so cap at 32
+    cores = min(os.cpu_count() or 1, 32)
     torch.set_num_threads(cores)
     # Bounded sample (~20-30 s of CPU work): ONE frame of the 16-frame window at 128x256 through one U-Net step and
     # each VAE pass.  Every stage's cost is linear in frames and (to first order) in pixels -- the spatial
