@@ -34,6 +34,28 @@ def test_postprocess_and_raymap_vs_oracle(cuda_device):
     assert torch.allclose(traj.cpu(), ref["traj"], atol=2e-4)
 
 
+def test_postprocess_and_raymap_vs_reference_golden(cuda_device, golden_dir):
+    """the same two kernels against the committed outputs of the reference's own post-processing functions
+    (tests/golden/post_ref.pt, oracle/gen_golden_post.py)"""
+    import os
+    from geo4d_b200.pipeline import raymap_to_camera_matrix
+    from geo4d_b200 import ops
+    ref = torch.load(os.path.join(golden_dir, "post_ref.pt"))
+    for name, r in ref.items():
+        maps = r["maps"]
+        T, H, W = maps.shape[2:]
+        md = maps.to(cuda_device)
+        valid = torch.ones(T, H, W, dtype=torch.uint8, device=cuda_device)
+        pts, conf, invd = ops.postprocess_window(md[0].contiguous(), T, H, W, valid=valid)
+        traj = raymap_to_camera_matrix(md[:, 4:7], md[:, 7:10])
+        torch.cuda.synchronize()
+        assert torch.allclose(pts.cpu(), r["pts3d"], atol=1e-6), name
+        assert torch.allclose(conf.cpu(), r["conf"], rtol=1e-5, atol=1e-6), name
+        assert torch.allclose(invd.cpu(), r["inverse_depthmap"], atol=1e-6), name
+        assert torch.equal(valid.cpu().bool().unsqueeze(-1), r["valid"]), name
+        assert torch.allclose(traj.cpu(), r["traj"], atol=5e-4), name
+
+
 def test_umeyama_kernel_vs_oracle(cuda_device):
     from oracle import align as oa
     from geo4d_b200.cloud_opt import umeyama_from_moments

@@ -126,3 +126,20 @@ def test_aligner_oracle_matches_reference_golden(golden_dir):
     assert float((r["poses"] - ref["poses"]).abs().max()) < 1e-3
     assert abs(r["focal"] - ref["focal"]) / ref["focal"] < 1e-3
     assert float((r["s_depth"] - ref["s_depth"]).abs().max()) < 1e-2
+
+
+def test_postprocess_and_raymap_match_reference_golden(golden_dir):
+    """oracle.align.postprocess_window / raymap_to_camera_matrix vs the outputs of the reference's OWN functions
+    (infer_geo4d.py get_sky_mask / get_far_away_mask / denormalize_pc_bbox2 / raymap_to_camera_matrix ->
+    utils.rays.cameras_from_plucker), generated by oracle/gen_golden_post.py."""
+    import os
+    ref = torch.load(os.path.join(golden_dir, "post_ref.pt"))
+    assert set(ref) == {"wide", "tall", "wide16"}
+    for name, r in ref.items():
+        o = oa.postprocess_window(r["maps"])
+        assert torch.equal(o["pts3d"], r["pts3d"]), name
+        assert torch.equal(o["conf"], r["conf"]), name
+        assert torch.equal(o["inverse_depthmap"], r["inverse_depthmap"]), name
+        assert torch.equal(o["valid"], r["valid"]), name
+        assert float((~r["valid"]).float().mean()) > 0.1          # the masks are actually exercised
+        assert float((o["traj"] - r["traj"]).abs().max()) < 5e-6, name
