@@ -32,6 +32,30 @@ class GemmDesc(C.Structure):
     ]
 
 
+class AlignLoopDesc(C.Structure):
+    """g4_align_loop_desc of include/geo4d_b200.h (field order and types must match)."""
+    _fields_ = [
+        ("logd", C.c_void_p), ("adam_m", C.c_void_p), ("adam_v", C.c_void_p),
+        ("pred", C.c_void_p), ("weight", C.c_void_p), ("invd", C.c_void_p),
+        ("edge_ptr", C.c_void_p), ("edge_idx", C.c_void_p), ("scal", C.c_void_p),
+        ("poses", C.c_void_p), ("S", C.c_void_p), ("invf", C.c_void_p), ("st", C.c_void_p),
+        ("gpose", C.c_void_p), ("gS", C.c_void_p), ("gscal", C.c_void_p), ("gst", C.c_void_p),
+        ("part", C.c_void_p), ("bar", C.c_void_p),
+        ("im_poses", C.c_void_p), ("im_focal", C.c_void_p), ("pw_poses", C.c_void_p), ("s_depth", C.c_void_p),
+        ("t_depth", C.c_void_p), ("ta_poses", C.c_void_p), ("adam_small", C.c_void_p),
+        ("traj", C.c_void_p), ("e_img", C.c_void_p), ("valid_traj", C.c_void_p),
+        ("N", C.c_int), ("G", C.c_int), ("HW", C.c_int), ("W", C.c_int), ("group_size", C.c_int),
+        ("max_edges_per_image", C.c_int),
+        ("n_lo", C.c_int), ("n_hi", C.c_int), ("chunks", C.c_int), ("it0", C.c_int), ("it1", C.c_int),
+        ("start_b", C.c_int),
+        ("temporal_smoothing_weight", C.c_float), ("translation_weight", C.c_float), ("base_scale", C.c_float),
+        ("focal_break", C.c_float),
+        ("world", C.c_int), ("rank", C.c_int), ("img_lo", C.c_int * 17), ("rec_doubles", C.c_int),
+        ("peer_rec", C.c_void_p * 16), ("peer_flag", C.c_void_p * 16),
+        ("flag_base", C.c_ulonglong),
+    ]
+
+
 _lib = None
 
 

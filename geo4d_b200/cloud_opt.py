@@ -82,6 +82,8 @@ def poses_from_params(p):
 def umeyama_from_moments(m0: np.ndarray, m1: np.ndarray):
     """(sum w, sum w x, sum w y) and (sum w|x^|^2, sum w y^ x^T) -> (s, R, T) with y ~ s R x + T."""
     sw = m0[0]
+    if not (np.isfinite(m0).all() and np.isfinite(m1).all() and sw > 0 and m1[0] > 0):
+        return float("nan"), np.eye(3), np.zeros(3)   # no overlap / all-zero weights: the caller applies its guard
     xm, ym = m0[1:4] / sw, m0[4:7] / sw
     M = m1[1:10].reshape(3, 3)
     U, D, Vt = np.linalg.svd(M)
@@ -118,7 +120,7 @@ class LightPointCloudGroupOptimizer(nn.Module):
                  temporal_smoothing_weight=0, translation_weight=0.1, flow_loss_start_epoch=0.15, flow_loss_thre=50,
                  sintel_ckpt=False, use_self_mask=False, pxl_thre=50, sam2_mask_refine=True, motion_mask_thre=0.35,
                  conf_optimize=False, depth_traj_start_iter=150, use_cuda_graph=True, lad_max_iters=5000,
-                 shard_sub_alignments=True):
+                 shard_sub_alignments=True, engine=None, shard_alignment=True):
         super().__init__()
         if dist != "l1" or conf not in ("id", "none") or not shared_focal or not conf_optimize or opt_raydir \
                 or optimize_pp or allow_pw_adaptors or flow_loss_weight != 0.0 or depth_regularize_weight != 0.0:
@@ -148,6 +150,15 @@ class LightPointCloudGroupOptimizer(nn.Module):
         self.use_cuda_graph = use_cuda_graph and os.environ.get("GEO4D_ALIGN_EAGER", "0") != "1"
         self.lad_max_iters = lad_max_iters
         self.shard_sub_alignments = shard_sub_alignments  # split per-window LAD fits over torch.distributed ranks
+        # "loop": the whole optimisation loop is one persistent cooperative kernel per phase (geo4d_align_loop);
+        # "steps": two kernels per iteration (geo4d_align_iter + geo4d_align_small_step), CUDA-graph replayed
+        self.engine = engine or os.environ.get("GEO4D_ALIGN_ENGINE", "loop")
+        if self.engine not in ("loop", "steps"):
+            raise ValueError(f"engine={self.engine!r}: 'loop' or 'steps'")
+        # under torch.distributed the images of the loop engine are sharded over the ranks (peer-to-peer exchange
+        # of the reduced gradients inside the kernel); False = every rank optimises the whole clip (replicated)
+        self.shard_alignment = shard_alignment
+        self._shard = None
         self._profile = None
         dev = p0.device
         G, gs, N, HW = self.n_groups, self.group_size, self.n_imgs, self.HW
@@ -275,12 +286,13 @@ class LightPointCloudGroupOptimizer(nn.Module):
         return [np.stack([c2w_to_tumpose(p) for p in poses], 0), np.arange(len(poses)).astype(float)]
 
     def save_tum_poses(self, path):
-        traj, tt = self.get_tum_poses()
-        with open(path, "w") as f:  # vo_eval.py:465-473 (TUM: timestamp tx ty tz qx qy qz qw)
-            for i in range(len(tt)):
-                p = traj[i]
-                f.write(f"{tt[i]} {p[0]} {p[1]} {p[2]} {p[4]} {p[5]} {p[6]} {p[3]}\n")
-        return traj
+        """base_opt_group.py:390-393 -> vo_eval.save_trajectory_tum_format (:465-473): one line per pose
+        `timestamp x y z qw qx qy qz` -- the quaternion stays in the wxyz order get_tum_poses returns (the
+        reference's viewer reads column 4 as w)."""
+        from .metrics import save_trajectory_tum_format
+        traj = self.get_tum_poses()
+        save_trajectory_tum_format(traj, path)
+        return traj[0]
 
     def save_focals(self, path):
         focals = self.get_focals()
@@ -293,10 +305,39 @@ class LightPointCloudGroupOptimizer(nn.Module):
         return K
 
     def save_depth_maps(self, path):
+        """base_opt_group.py:433-464: frame_%04d.npy (depth), frame_colordepth_%04d.png (inverse depth, 2-98
+        percentile window over the sequence, inferno colour map) and colored_depth_maps.gif.  The reference takes
+        the colour table from matplotlib (cm.get_cmap('inferno').colors, truncated to 8 bits); matplotlib is not a
+        dependency here, so the same published table is taken from OpenCV (COLORMAP_INFERNO, rounded to 8 bits):
+        colours may differ by one code value."""
+        import cv2
         dms = self.get_depthmaps()
         for i, d in enumerate(dms):
             np.save(f"{path}/frame_{i:04d}.npy", d.detach().cpu().numpy())
-        return dms
+        inv = (1.0 / (self.get_depthmaps(raw=True).reshape(-1, self.H, self.W) + 1e-6)).cpu().numpy()
+        v_min, v_max = np.percentile(inv, 2), np.percentile(inv, 98)
+        idx = np.clip(((inv - v_min) / (v_max - v_min) * 255).astype(np.int64), 0, 255).astype(np.uint8)
+        frames = []
+        for i, im in enumerate(idx):
+            bgr = cv2.applyColorMap(im, cv2.COLORMAP_INFERNO)
+            cv2.imwrite(f"{path}/frame_colordepth_{i:04d}.png", bgr)
+            frames.append(cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB))
+        try:
+            from PIL import Image
+            ims = [Image.fromarray(f) for f in frames]
+            ims[0].save(f"{path}/colored_depth_maps.gif", save_all=True, append_images=ims[1:], duration=100, loop=0)
+        except ImportError:  # pragma: no cover
+            pass
+        return torch.from_numpy(inv)
+
+    def save_rgb_imgs(self, path):
+        """base_opt_group.py:419-425: frame_%04d.png of the input frames (RGB in [0, 1] -> BGR 8 bit)."""
+        import cv2
+        if self.imgs is None:
+            raise ValueError("save_rgb_imgs: the views carried no 'img' entries")
+        for i, img in enumerate(self.imgs):
+            cv2.imwrite(f"{path}/frame_{i:04d}.png", np.ascontiguousarray(img[..., ::-1]) * 255)
+        return self.imgs
 
     def save_conf_maps(self, path):
         for i, c in enumerate(self.im_conf):
@@ -322,7 +363,18 @@ class LightPointCloudGroupOptimizer(nn.Module):
         m0 = ops.umeyama_moments(x, y, w1, w2, n, 0, None)
         means = (m0[1:7] / m0[0]).contiguous()
         m1 = ops.umeyama_moments(x, y, w1, w2, n, 1, means)
-        return umeyama_from_moments(m0.cpu().numpy(), m1.cpu().numpy())
+        s, R, T = umeyama_from_moments(m0.cpu().numpy(), m1.cpu().numpy())
+        # Degenerate registrations (uncorrelated point sets, e.g. the output of a randomly initialised network:
+        # the fitted scale decays geometrically along the window chain until the fp32 point maps underflow to 0)
+        # would make the reference write log(0) = -inf into pw_poses and carry NaNs from there on; a floor keeps
+        # every later stage finite.  It never binds on registrable windows (s ~ 1).
+        if not (s > 1e-12) or not math.isfinite(s):
+            s = 1e-12
+        if not np.all(np.isfinite(R)):
+            R = np.eye(3)
+        if not np.all(np.isfinite(T)):
+            T = np.zeros(3)
+        return s, R, T
 
     @staticmethod
     def _set_pose(poses, idx, R, T, scale=None, scale_T=True):
@@ -330,9 +382,10 @@ class LightPointCloudGroupOptimizer(nn.Module):
             poses[idx, 0:4] = torch.as_tensor(rotmat_to_unitquat_np(np.asarray(R, dtype=np.float64)),
                                               dtype=poses.dtype, device=poses.device)
             Tt = torch.as_tensor(np.asarray(T, dtype=np.float64), dtype=poses.dtype, device=poses.device)
-            poses[idx, 4:7] = signed_log1p(Tt / (scale if (scale is not None and scale_T) else 1))
+            poses[idx, 4:7] = signed_log1p(Tt / ((scale or 1) if scale_T else 1))   # base_opt_group.py:280-283
             if scale is not None:
-                poses[idx, -1] = math.log(float(scale))
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    poses[idx, -1] = float(np.log(float(scale)))                       # :287 (numpy: log 0 = -inf)
 
     @torch.no_grad()
     def _init_from_group(self, niter_PnP=10):
@@ -363,9 +416,10 @@ class LightPointCloudGroupOptimizer(nn.Module):
         im_poses: List[Optional[np.ndarray]] = [None] * N
         im_focals: List[Optional[float]] = [None] * N
         done = set()
+        chain_pnp = host_solvers or os.environ.get("GEO4D_INIT_PNP", "window") == "chain"
 
         def pnp_frames(frame_ids, pts_gpu, conf_gpu, first_focal_of):
-            """per-frame pose + focal (fast_pnp, init_im_poses.py:824-865)"""
+            """per-frame pose + focal (fast_pnp, init_im_poses.py:824-865) on world-frame points, frame by frame"""
             if host_solvers:
                 pts_cpu = pts_gpu.reshape(-1, H, W, 3).cpu().numpy()
                 msk_cpu = (conf_gpu > 0.5).reshape(-1, H, W).cpu().numpy()
@@ -379,11 +433,48 @@ class LightPointCloudGroupOptimizer(nn.Module):
                 isv.gpu_fast_pnp_frames(ops, pts_gpu.contiguous(), conf_gpu.contiguous(), H, W, first_focal_of,
                                         im_focals, im_poses, frame_ids, niter_PnP)
 
+        # Stage 1 (default): PnP of every frame in its window's OWN frame.  Windows are independent there, so under
+        # torch.distributed rank r solves the windows g with g % world == r and the (focal, pose) records are
+        # all-gathered; the sequential window chain below only composes them with each window's registration.
+        local = None
+        if not chain_pnp:
+            world, rank = 1, 0
+            if self.shard_sub_alignments and torch.distributed.is_available() and torch.distributed.is_initialized():
+                world, rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
+            from . import sharding
+            mine = sharding.windows_for_rank(G, rank, world) if world > 1 else list(range(G))
+            per = -(-G // world)
+            rec = torch.zeros(per, gs * 18, dtype=torch.float64, device=dev)
+            if mine:
+                idx = torch.tensor(mine, device=dev)
+                f_l, c_l, ok_l = isv.gpu_fast_pnp_windows(ops, pred[idx].contiguous(), conf[idx].contiguous(), H, W,
+                                                          [focal_group[g] for g in mine], niter_PnP)
+                r_np = np.concatenate([np.nan_to_num(f_l, nan=-1.0)[..., None], ok_l[..., None].astype(np.float64),
+                                       c_l.reshape(len(mine), gs, 16)], -1).reshape(len(mine), gs * 18)
+                rec[:len(mine)] = torch.from_numpy(r_np).to(dev)
+            full = (sharding.gather_group_records(rec, G) if world > 1 else rec[:G]).cpu().numpy().reshape(G, gs, 18)
+            local = (full[..., 0], full[..., 1] > 0.5, full[..., 2:].reshape(G, gs, 4, 4))
+
+        def compose(i, group, s_i, R_i, T_i):
+            """window-frame PnP results -> world frame through the window's registration y = s R x + T"""
+            f_l, ok_l, c_l = local
+            for k, img in enumerate(group):
+                if ok_l[i, k]:
+                    P = np.eye(4)
+                    P[:3, :3] = R_i @ c_l[i, k, :3, :3]
+                    P[:3, 3] = s_i * (R_i @ c_l[i, k, :3, 3]) + T_i
+                    im_focals[img], im_poses[img] = float(f_l[i, k]), P
+                if im_poses[img] is None:
+                    im_poses[img] = np.eye(4)
+
         g0 = self.groups[0]
         im_focals[g0[0]] = focal_group[0]
         pts3d[g0] = pred[0]
         conf_list[g0] = conf[0]
-        pnp_frames(g0, pred[0], conf[0], lambda k, img: im_focals[img - 1] if img != 0 else im_focals[img])
+        if chain_pnp:
+            pnp_frames(g0, pred[0], conf[0], lambda k, img: im_focals[img - 1] if img != 0 else im_focals[img])
+        else:
+            compose(0, g0, 1.0, np.eye(3), np.zeros(3))
         done.update(g0)
         for i in range(1, G):
             group = self.groups[i]
@@ -402,8 +493,11 @@ class LightPointCloudGroupOptimizer(nn.Module):
                 P = np.eye(4)
                 P[:3, :3], P[:3, 3] = R, T
                 im_poses[group[0]] = P
-            pnp_frames(group, new_pts, conf[i],
-                       lambda k, img, fg=focal_group[i]: fg if k == 0 else im_focals[img - 1])
+            if chain_pnp:
+                pnp_frames(group, new_pts, conf[i],
+                           lambda k, img, fg=focal_group[i]: fg if k == 0 else im_focals[img - 1])
+            else:
+                compose(i, group, s, R, T)
             done.update(group)
         im_poses_np = np.stack(im_poses)
         # init_from_pts3d_group (init_im_poses.py:569-633)
@@ -502,6 +596,14 @@ class LightPointCloudGroupOptimizer(nn.Module):
                     best_d1 = np.where(better, d1, best_d1)
             return best_st, best_d1
 
+        def solve_all(sel):
+            """the one-launch fit keeps a window's samples in shared memory only while (samples / SMs-per-window)
+            fits; several big windows on one GPU are therefore fitted one after the other, each on every SM"""
+            if len(sel) <= 1 or n * 8 * len(sel) <= 148 * 190 * 1024 or not self.use_cuda_graph:
+                return solve(sel)
+            parts = [solve([g]) for g in sel]
+            return torch.cat([p[0] for p in parts], 0), np.concatenate([p[1] for p in parts])
+
         world, rank = 1, 0
         if self.shard_sub_alignments and torch.distributed.is_available() and torch.distributed.is_initialized():
             world, rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
@@ -511,13 +613,13 @@ class LightPointCloudGroupOptimizer(nn.Module):
             mine = sharding.windows_for_rank(G, rank, world)
             rec = torch.zeros(per, 3, device=dev, dtype=torch.float64)
             if mine:
-                st, d1 = solve(mine)
+                st, d1 = solve_all(mine)
                 rec[:len(mine), :2] = st.double()
                 rec[:len(mine), 2] = torch.as_tensor(d1, device=dev, dtype=torch.float64)
             full = sharding.gather_group_records(rec, G)
             best_st, best_d1 = full[:, :2].float(), full[:, 2].cpu().numpy()
         else:
-            best_st, best_d1 = solve(list(range(G)))
+            best_st, best_d1 = solve_all(list(range(G)))
         self.s_depth.data[:, 0] = best_st[:, 0]
         self.t_depth.data[:, 0] = best_st[:, 1]
         return [int(i) for i in np.nonzero(best_d1 < 0.3)[0]]
@@ -696,6 +798,106 @@ class LightPointCloudGroupOptimizer(nn.Module):
             graph.replay()
         ops.note_replay(nk, it1 - it)
 
+    # ------------------------------------------------------------------ persistent loop engine
+    def _dist(self):
+        """(world, rank) of the sharded alignment, (1, 0) when it runs on one GPU / replicated."""
+        if self.shard_alignment and self.engine == "loop" and torch.distributed.is_available() \
+                and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1 \
+                and self.n_imgs >= 2 and os.environ.get("GEO4D_ALIGN_SHARD", "1") != "0":
+            return torch.distributed.get_world_size(), torch.distributed.get_rank()
+        return 1, 0
+
+    def _setup_loop(self, st):
+        """Buffers and the descriptor of geo4d_align_loop; under torch.distributed also the image partition and
+        the peer-mapped receive buffers of the in-kernel exchange."""
+        from . import sharding
+        from ._cabi import AlignLoopDesc
+        import ctypes as C
+        L = ops.lib()
+        L.geo4d_align_loop_part_floats.restype = C.c_size_t
+        dev = self.device
+        N, G, HW = self.n_imgs, self.n_groups, self.HW
+        if HW % 4:
+            raise NotImplementedError("engine='loop' needs H*W to be a multiple of 4 (Geo4D sizes are multiples of 16)")
+        world, rank = self._dist()
+        img_lo = [0, N]
+        ex = None
+        rec = 0
+        if world > 1:
+            edges = np.diff(self._edge_ptr.cpu().numpy()).tolist()
+            img_lo = sharding.partition_images(edges, world)
+            max_loc = max(img_lo[r + 1] - img_lo[r] for r in range(world))
+            rec = int(L.geo4d_align_loop_record_doubles(max_loc, G))
+            need = 256 + 2 * world * rec * 8
+            nbytes = max(1 << 20, 1 << (need - 1).bit_length())
+            ex = sharding.peer_exchange(nbytes, dev)
+            if ex is None:   # no peer-memory transport on this box: optimise the whole clip on every rank
+                world, rank, img_lo, rec = 1, 0, [0, N], 0
+        n_lo, n_hi = img_lo[rank], img_lo[rank + 1]
+        chunks = int(L.geo4d_align_loop_chunks(max(1, n_hi - n_lo), HW))
+        d = AlignLoopDesc()
+        st["loop_keep"] = keep = {
+            "part": torch.zeros(max(1, int(L.geo4d_align_loop_part_floats(max(1, n_hi - n_lo), chunks))), device=dev),
+            "bar": torch.zeros(2, device=dev, dtype=torch.int32),
+        }
+        P = ops._ptr
+        d.logd, d.adam_m, d.adam_v = P(self.im_depthmaps), P(st["m"]), P(st["v"])
+        d.pred, d.weight = P(self._stacked_pred_all), P(self._weight_all)
+        d.invd = P(self._stacked_depthmap_all) if self.has_invdepth else None
+        d.edge_ptr, d.edge_idx, d.scal = P(self._edge_ptr), P(self._edge_idx), P(st["scal"])
+        d.poses, d.S, d.invf, d.st = P(st["poses"]), P(st["S"]), P(st["invf"]), P(st["st"])
+        d.gpose, d.gS, d.gscal, d.gst = P(st["gpose"]), P(st["gS"]), P(st["gscal"]), P(st["gst"])
+        d.part, d.bar = P(keep["part"]), P(keep["bar"])
+        d.im_poses, d.im_focal, d.pw_poses = P(self.im_poses), P(self.im_focals), P(self.pw_poses)
+        d.s_depth, d.t_depth, d.ta_poses = P(self.s_depth), P(self.t_depth), P(self.traj_align_poses)
+        d.adam_small, d.traj, d.e_img, d.valid_traj = P(st["adam_small"]), P(st["traj16"]), P(st["e_img"]), P(st["valid_traj"])
+        d.N, d.G, d.HW, d.W, d.group_size = N, G, HW, self.W, self.group_size
+        d.max_edges_per_image = self.max_edges_per_image
+        d.n_lo, d.n_hi, d.chunks, d.start_b = n_lo, n_hi, chunks, st["start_b"]
+        d.temporal_smoothing_weight = self.temporal_smoothing_weight
+        d.translation_weight = self.translation_weight
+        d.base_scale, d.focal_break = self.base_scale, self.focal_break
+        d.world, d.rank, d.rec_doubles = world, rank, rec
+        for r in range(world + 1):
+            d.img_lo[r] = img_lo[r]
+        if ex is not None:
+            for r in range(world):
+                d.peer_flag[r] = ex.ptrs[r]
+                d.peer_rec[r] = ex.ptrs[r] + 256
+            d.flag_base = sharding.reserve_flags(self._niter_total)
+        st["loop_desc"] = d
+        self._shard = {"world": world, "rank": rank, "img_lo": img_lo, "transport": ex.how if ex else None}
+
+    def _run_loop(self, st, it0, it1):
+        if it1 <= it0:
+            return
+        if "loop_desc" not in st:
+            self._setup_loop(st)
+        self._refresh_matrices(st)
+        d = st["loop_desc"]
+        d.it0, d.it1 = it0, it1
+        import ctypes as C
+        ops.check(ops.lib().geo4d_align_loop(C.byref(d), ops._s()), "geo4d_align_loop")
+
+    @torch.no_grad()
+    def _broadcast_state(self):
+        """Sharded alignment: every rank starts from rank 0's initialisation (the GPU reductions of the
+        initialisation use atomics, so replicas could differ in the last bit)."""
+        for t in (self.im_depthmaps, self.im_poses, self.im_focals, self.pw_poses):
+            torch.distributed.broadcast(t.data, src=0)
+
+    @torch.no_grad()
+    def _gather_depth(self):
+        """Sharded alignment: every rank owns the log-depth maps of its images; make them complete everywhere."""
+        sh = self._shard
+        if not sh or sh["world"] <= 1:
+            return
+        lo, hi = sh["img_lo"][sh["rank"]], sh["img_lo"][sh["rank"] + 1]
+        d = self.im_depthmaps.data
+        d[:lo].zero_()
+        d[hi:].zero_()
+        torch.distributed.all_reduce(d)
+
     @torch.no_grad()
     def _current_loss(self, st, phase_b) -> float:
         """Objective value at the current parameters (optimizer_group.py:523), from the kernel's reductions."""
@@ -779,13 +981,21 @@ class LightPointCloudGroupOptimizer(nn.Module):
             st["start_b"] = int(start_b)
         with torch.no_grad():
             self._weight_all.clamp_(max=10)  # conf_optimize clip, optimizer_group.py:455-456
+        loop = fused and self.engine == "loop"
+        self._niter_total = int(niter)
+        if loop and self._dist()[0] > 1:
+            self._broadcast_state()
         with torch.enable_grad():
-            if fused:
+            if loop:
+                self._run_loop(st, 0, min(start_b, niter))
+            elif fused:
                 self._run_phase_fused(st, 0, min(start_b, niter))
             else:
                 self._run_phase(st, 0, min(start_b, niter), False)
             self._tick("phase_A")
             if niter > start_b:
+                if loop:
+                    self._gather_depth()
                 if self.has_invdepth:
                     self.invalid_depth_group = self._set_st_depth()
                     self._tick("set_st_depth(LAD)")
@@ -803,10 +1013,15 @@ class LightPointCloudGroupOptimizer(nn.Module):
                 if fused:
                     if self.has_traj and self.valid_traj_group_list:
                         st["valid_traj"][self.valid_traj_group_list] = 1.0
-                    self._run_phase_fused(st, start_b, niter)
+                    if loop:
+                        self._run_loop(st, start_b, niter)
+                    else:
+                        self._run_phase_fused(st, start_b, niter)
                 else:
                     self._run_phase(st, start_b, niter, True)
                 self._tick("phase_B")
+        if loop:
+            self._gather_depth()
         torch.cuda.synchronize()
         if self._profile is not None:
             print("align profile:", ", ".join(f"{n}={t * 1e3:.1f}ms" for n, t in self._profile))

@@ -387,6 +387,79 @@ def gpu_fast_pnp_frames(ops, pts: "torch.Tensor", conf: "torch.Tensor", H: int, 
             im_poses[img] = np.eye(4)
 
 
+def gpu_fast_pnp_windows(ops, pred: "torch.Tensor", conf: "torch.Tensor", H: int, W: int, focal_group,
+                         niter_PnP: int = 10, thr_px: float = 5.0):
+    """fast_pnp (init_im_poses.py:824-865) for every frame of several windows, each in its window's OWN frame.
+
+    pred [Gm, gs, HW, 3], conf [Gm, gs, HW]: the windows this rank initialises.  PnP is equivariant under the
+    window's sim(3) registration (a point map s R X + T seen through the same pixels gives the camera
+    [R_c2w' | t'] = [R R_c2w | s R t_c2w + T], identical consensus sets), so it does not have to wait for the
+    sequential window chain of align_group_prefix: windows are independent here, which is what lets the ranks
+    split them, and frame k of all Gm windows shares ONE moments launch and ONE device -> host read.
+    Inside a window the reference's focal chain is kept: frame 0 starts from the window's focal (the LM fit),
+    frame k from frame k-1's result (after a failed PnP: the last successful one in this window).
+
+    Returns (focals [Gm, gs] (nan = PnP failed), c2w [Gm, gs, 4, 4] (window frame), ok [Gm, gs] bool)."""
+    import torch
+    Gm, gs = int(pred.shape[0]), int(pred.shape[1])
+    HW = H * W
+    cx, cy = W / 2, H / 2
+    S = max(W, H)
+    dev = pred.device
+    # frame-major copies: frame k of every window contiguous
+    pts_t = pred.transpose(0, 1).contiguous()      # [gs, Gm, HW, 3]
+    conf_t = conf.transpose(0, 1).contiguous()     # [gs, Gm, HW]
+    mom_all = ops.pnp_moments(pts_t.view(gs * Gm, HW, 3), conf_t.view(gs * Gm, HW), gs * Gm, HW, W, cx, cy) \
+        .cpu().numpy()[:, 0].reshape(gs, Gm, -1)   # focal-independent moments of every frame, one read
+    focals = np.full((Gm, gs), np.nan)
+    c2w = np.tile(np.eye(4), (Gm, gs, 1, 1))
+    ok = np.zeros((Gm, gs), dtype=bool)
+    prev = [float(f) if f is not None and np.isfinite(f) and f > 0 else None for f in focal_group]
+    for k in range(gs):
+        tent = []
+        for g in range(Gm):
+            focal = prev[g]
+            if focal is None:
+                t = list(np.geomspace(S / 2, S * 3, 63))
+            else:
+                lo, hi = -0.03 * S + focal, 0.03 * S + focal
+                t = [focal] + ([float(x) for x in np.geomspace(lo, hi, 2)] if lo > 0 else [])
+            tent.append([float(f) for f in t if np.isfinite(f) and f > 0])
+        sols = [sqpnp_from_moments_batch(np.repeat(mom_all[k, g][None], len(tent[g]), 0), tent[g]) for g in range(Gm)]
+        good = [[i for i, sol in enumerate(sols[g]) if sol is not None] for g in range(Gm)]
+        C = max((len(x) for x in good), default=0)
+        if C == 0:
+            continue
+        gate = np.zeros((Gm, C, 13), dtype=np.float32)
+        gate[:, :, 11] = -1.0                      # padding candidates: R = 0, t_z = -1 puts every point behind the camera
+        gate[:, :, 12] = 1.0
+        for g in range(Gm):
+            for j, i in enumerate(good[g]):
+                R, t = sols[g][i]
+                gate[g, j, :12] = np.concatenate([R, t[:, None]], 1).reshape(12)
+                gate[g, j, 12] = tent[g][i]
+        mom_in = ops.pnp_moments(pts_t[k], conf_t[k], Gm, HW, W, cx, cy, gate=torch.from_numpy(gate).to(dev), ncand=C,
+                                 thr_px=thr_px).cpu().numpy()
+        for g in range(Gm):
+            if not good[g]:
+                continue
+            refit = sqpnp_from_moments_batch(mom_in[g, :len(good[g])], [tent[g][i] for i in good[g]])
+            best = (0, None, None)
+            for j, i in enumerate(good[g]):
+                ninl = int(round(mom_in[g, j, 40]))
+                if ninl < 4 or ninl <= best[0]:
+                    continue
+                if refit[j] is not None:
+                    best = (ninl, refit[j], tent[g][i])
+            if best[0]:
+                R, t = best[1]
+                w2c = np.eye(4)
+                w2c[:3, :3], w2c[:3, 3] = R, t
+                focals[g, k], c2w[g, k], ok[g, k] = best[2], np.linalg.inv(w2c), True
+                prev[g] = float(best[2])
+    return focals, c2w, ok
+
+
 def gpu_focal_per_group(ops, ref_pts: "torch.Tensor", ref_conf: "torch.Tensor", H: int, W: int):
     """focal_per_group with the sums on the GPU: 1-D damped Newton on the z-shift from s = 0 (the reference runs
     scipy's LM from the same start; both stop at the local minimiser of sum |f p - uv|^2)."""

@@ -4,7 +4,7 @@ per-window post-processing; the only exchange is one all-gather of the fixed-siz
 GPU; NCCL over NVLink on the GPU box, gloo in the CPU tests."""
 from __future__ import annotations
 
-from typing import Dict, List, Sequence
+from typing import Dict, List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
@@ -70,3 +70,103 @@ def gather_group_records(local: torch.Tensor, n_groups: int, group=None) -> torc
     dist.all_gather_into_tensor(allrec, local.contiguous(), group=group)
     allrec = allrec.view((world, per) + tuple(local.shape[1:]))
     return torch.stack([allrec[g % world, g // world] for g in range(n_groups)])
+
+
+# ----------------------------------------------------------------------------------------------- alignment sharding
+def partition_images(edges_per_image: Sequence[int], world: int) -> List[int]:
+    """Contiguous image ranges per rank for the sharded alignment loop, balanced by per-pixel work
+    (1 + number of windows observing the image).  Returns img_lo with world + 1 entries."""
+    cost = [1 + int(e) for e in edges_per_image]
+    n, total = len(cost), float(sum(cost))
+    lo, acc, r = [0], 0.0, 1
+    for i, c in enumerate(cost):
+        acc += c
+        while r < world and acc >= total * r / world - 1e-9 and (n - (i + 1)) >= 0:
+            lo.append(i + 1)
+            r += 1
+    while len(lo) < world + 1:
+        lo.append(n)
+    lo[world] = n
+    return lo
+
+
+class PeerExchange:
+    """One receive buffer per rank, mapped into every rank's address space so that a kernel can store straight
+    into its peers' memory over NVLink (the exchange step of geo4d_align_loop).  Mapping goes through
+    torch.distributed._symmetric_memory (CUDA VMM handles) and, if that is unavailable, through classic CUDA IPC
+    handles (torch storage sharing).  `ptrs[r]` is the address of rank r's buffer as seen from THIS process."""
+
+    def __init__(self, nbytes: int, device: torch.device, group=None):
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.nbytes = nbytes
+        self.how = None
+        self._keep = []
+        err = []
+        for how in ("symm", "ipc"):
+            try:
+                getattr(self, "_open_" + how)(nbytes, device, group)
+                self.how = how
+                break
+            except Exception as ex:  # noqa: BLE001 -- any failure selects the next transport
+                err.append(f"{how}: {type(ex).__name__}: {ex}")
+        ok = torch.tensor([1 if self.how else 0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok) == 0 or self.how is None:
+            raise RuntimeError("no peer-memory transport available: " + " | ".join(err))
+        self.local.zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier(group)
+
+    def _open_symm(self, nbytes, device, group):
+        import torch.distributed._symmetric_memory as symm
+        t = symm.empty(nbytes, dtype=torch.uint8, device=device)
+        hdl = symm.rendezvous(t, group if group is not None else dist.group.WORLD)
+        self.local = t
+        self.ptrs = [int(p) for p in hdl.buffer_ptrs]
+        self._keep.append(hdl)
+        assert self.ptrs[self.rank] == t.data_ptr()
+
+    def _open_ipc(self, nbytes, device, group):
+        t = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        handle = t.untyped_storage()._share_cuda_()
+        off = t.storage_offset()
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (handle, off), group=group)
+        self.local = t
+        self.ptrs = []
+        for r, (h, o) in enumerate(handles):
+            if r == self.rank:
+                self.ptrs.append(t.data_ptr())
+                continue
+            st = torch.UntypedStorage._new_shared_cuda(*h)
+            peer = torch.empty(0, dtype=torch.uint8, device=st.device).set_(st, o, (nbytes,))
+            torch.zeros(8, dtype=torch.uint8, device=device).copy_(peer[:8])   # makes torch enable P2P access
+            self._keep.append((st, peer))
+            self.ptrs.append(peer.data_ptr())
+
+
+_exchange_cache: Dict[tuple, "PeerExchange"] = {}
+_flag_epoch = 0
+
+
+def peer_exchange(nbytes: int, device: torch.device, group=None) -> Optional["PeerExchange"]:
+    """Cached PeerExchange of at least nbytes, or None when no transport works on this box (the caller then runs
+    the alignment replicated).  Collective: every rank must call it with the same size."""
+    key = (device.index, dist.get_world_size(group), nbytes)
+    if key not in _exchange_cache:
+        try:
+            _exchange_cache[key] = PeerExchange(nbytes, device, group)
+        except Exception as ex:  # noqa: BLE001
+            import warnings
+            warnings.warn(f"geo4d_b200: sharded alignment disabled ({ex})")
+            _exchange_cache[key] = None
+    return _exchange_cache[key]
+
+
+def reserve_flags(count: int) -> int:
+    """Monotonic flag values for the next `count` iterations (identical on every rank: same call sequence)."""
+    global _flag_epoch
+    base = _flag_epoch
+    _flag_epoch += count + 8
+    return base

@@ -230,6 +230,42 @@ int geo4d_align_small_step(float* im_poses, float* im_focal, float* pw_poses, fl
                            int group_size, int start_b, float temporal_smoothing_weight, float translation_weight,
                            float base_scale, float focal_break, g4_stream_t stream);
 
+/* The whole optimisation loop of LightPointCloudGroupOptimizer.compute_global_alignment for iterations
+ * [it0, it1) (base_opt_group.py:553-626 driving optimizer_group.py:440-525) in ONE persistent cooperative
+ * launch: dense per-pixel part (same arithmetic as geo4d_align_iter) -> grid barrier -> deterministic fold of
+ * the per-unit partial sums -> (multi-GPU: images [n_lo, n_hi) of this rank; every rank's record is stored
+ * straight into each peer's receive buffer over NVLink and summed in rank order) -> the O(N + G) step of
+ * geo4d_align_small_step -> grid barrier.  Replaces (it1 - it0) x {geo4d_align_iter, geo4d_align_small_step}.
+ * All pointers are device pointers owned by the caller; peer_rec / peer_flag are peer-mapped addresses
+ * (cudaIpc / symmetric memory) of every rank's receive buffer ([2][world][rec_doubles] doubles) and flag
+ * array ([world] uint64), world == 1 ignores them.  Flags carry flag_base + it + 1 and must grow
+ * monotonically over the calls that share the buffers.  part: geo4d_align_loop_part_floats(n_hi - n_lo, chunks)
+ * floats; bar: two zero-initialised uint32 (kept between calls).  HW must be a multiple of 4. */
+typedef struct g4_align_loop_desc {
+  float* logd; float* adam_m; float* adam_v;        /* [N][HW] log-depth and its Adam moments */
+  const float* pred; const float* weight; const float* invd;   /* [E][HW][3], [E][HW], [E][HW] | NULL */
+  const int* edge_ptr; const int* edge_idx;         /* image -> incident (window, frame) edges, CSR */
+  const float* scal;                                /* [iters][8] per-iteration constants (see csrc/align.cu) */
+  float* poses; float* S; float* invf; float* st;   /* [N][12], [G][12], [1], [G][3]: current matrices (in/out) */
+  double* gpose; double* gS; double* gscal; double* gst;   /* [N][12], [G][12], [3], [G][2]: totals of the last iteration */
+  float* part; unsigned int* bar;
+  float* im_poses; float* im_focal; float* pw_poses; float* s_depth; float* t_depth; float* ta_poses;   /* parameters */
+  float* adam_small;                                /* geo4d_align_small_adam_floats(N, G) floats */
+  const float* traj; const int* e_img; const float* valid_traj;   /* [E][16], [E], [G] */
+  int N, G, HW, W, group_size, max_edges_per_image;
+  int n_lo, n_hi, chunks, it0, it1, start_b;
+  float temporal_smoothing_weight, translation_weight, base_scale, focal_break;
+  int world, rank;
+  int img_lo[17];                                   /* image partition: rank r owns [img_lo[r], img_lo[r+1]) */
+  int rec_doubles;                                  /* geo4d_align_loop_record_doubles(max images per rank, G) */
+  void* peer_rec[16]; void* peer_flag[16];
+  unsigned long long flag_base;
+} g4_align_loop_desc;
+size_t geo4d_align_loop_part_floats(int n_images_local, int chunks);
+int geo4d_align_loop_record_doubles(int max_images_per_rank, int G);
+int geo4d_align_loop_chunks(int n_images_local, int HW);
+int geo4d_align_loop(const g4_align_loop_desc* d, g4_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -149,8 +149,8 @@ def test_lad_single_launch_matches_stepwise(cuda_device, G, n):
     assert float((a[:, :2] - b[:, :2]).abs().max()) < 1e-4
 
 
-@pytest.mark.parametrize("graph", [False, True])
-def test_aligner_vs_oracle(cuda_device, graph):
+@pytest.mark.parametrize("engine,graph", [("steps", False), ("steps", True), ("loop", True)])
+def test_aligner_vs_oracle(cuda_device, engine, graph):
     from oracle import align as oa
     from geo4d_b200.cloud_opt import LightPointCloudGroupOptimizer
     groups, preds, gt = oa.synthetic_scene(T=24, H=32, W=48, noise=0.003)
@@ -163,7 +163,7 @@ def test_aligner_vs_oracle(cuda_device, graph):
     scene = LightPointCloudGroupOptimizer(views, preds_d, conf="id", conf_optimize=True, verbose=False,
                                           shared_focal=True, num_total_iter=niter, temporal_smoothing_weight=0.015,
                                           translation_weight=1.0, depth_traj_start_iter=start_b, lad_max_iters=lad,
-                                          use_cuda_graph=graph)
+                                          use_cuda_graph=graph, engine=engine)
     with torch.enable_grad():
         scene.compute_global_alignment(init="group", niter=niter, schedule="linear", lr=0.03)
     assert scene.invalid_depth_group == ref.invalid_depth_group
@@ -227,17 +227,17 @@ def test_gpu_pnp_and_focal_solvers_vs_cv2_scipy(cuda_device):
         assert abs(a - b) / a < 1e-2, (host, dev)
 
 
-def _run_small(mode, monkeypatch, cuda_device, niter, start_b, graph=False):
+def _run_small(mode, monkeypatch, cuda_device, niter, start_b, graph=False, engine="steps", T=24, H=32, W=48):
     from oracle import align as oa
     from geo4d_b200.cloud_opt import LightPointCloudGroupOptimizer
-    groups, preds, _ = oa.synthetic_scene(T=24, H=32, W=48, noise=0.003)
+    groups, preds, _ = oa.synthetic_scene(T=T, H=H, W=W, noise=0.003)
     views = [[{"idx": (i,)} for i in g] for g in groups]
     monkeypatch.setenv("GEO4D_ALIGN_AUTOGRAD", mode)
     preds_d = [{k: v.to(cuda_device) for k, v in p.items()} for p in preds]
     sc = LightPointCloudGroupOptimizer(views, preds_d, conf="id", conf_optimize=True, verbose=False,
                                        shared_focal=True, num_total_iter=niter, temporal_smoothing_weight=0.015,
                                        translation_weight=1.0, depth_traj_start_iter=start_b, lad_max_iters=300,
-                                       use_cuda_graph=graph)
+                                       use_cuda_graph=graph, engine=engine)
     with torch.enable_grad():
         loss = sc.compute_global_alignment(init="group", niter=niter, schedule="linear", lr=0.03)
     return sc, loss
@@ -309,3 +309,36 @@ def test_fused_small_parameter_kernel_trajectory(cuda_device, monkeypatch):
     assert abs(la - lf) / la < 0.1, (la, lf)
     da, df = torch.stack(a.get_depthmaps()).cpu(), torch.stack(f.get_depthmaps()).cpu()
     assert float(((da - df).abs() / da).mean()) < 2e-2
+
+
+def test_loop_engine_matches_stepwise_and_is_bit_reproducible(cuda_device, monkeypatch):
+    """geo4d_align_loop (one persistent cooperative launch per phase, deterministic fold of the per-unit partial
+    sums) runs the same arithmetic as iterations x {geo4d_align_iter, geo4d_align_small_step}: phase A follows the
+    stepwise trajectory to fp32 rounding (only the summation order of the reductions differs); across the phase
+    boundary the objective and the geometry agree; and two runs of the loop engine are bit-identical (the
+    stepwise engine accumulates with fp64 atomics and is not)."""
+    a, _ = _run_small("0", monkeypatch, cuda_device, niter=20, start_b=20, graph=True, engine="steps")
+    f, _ = _run_small("0", monkeypatch, cuda_device, niter=20, start_b=20, engine="loop")
+    for name in ("im_poses", "im_focals", "pw_poses", "im_depthmaps"):
+        d = float((getattr(a, name).detach() - getattr(f, name).detach()).abs().max())
+        assert d < 2e-4, (name, d)
+    a, la = _run_small("0", monkeypatch, cuda_device, niter=60, start_b=20, graph=True, engine="steps")
+    f, lf = _run_small("0", monkeypatch, cuda_device, niter=60, start_b=20, engine="loop")
+    g, lg = _run_small("0", monkeypatch, cuda_device, niter=60, start_b=20, engine="loop")
+    assert abs(la - lf) / la < 0.1, (la, lf)
+    da, df = torch.stack(a.get_depthmaps()).cpu(), torch.stack(f.get_depthmaps()).cpu()
+    assert float(((da - df).abs() / da).mean()) < 2e-2
+    assert lf == lg
+    for name in SMALL + ["im_depthmaps"]:
+        assert torch.equal(getattr(f, name).detach(), getattr(g, name).detach()), name
+
+
+@pytest.mark.parametrize("T,H,W", [(16, 16, 24), (40, 32, 48)])
+def test_loop_engine_shapes(cuda_device, monkeypatch, T, H, W):
+    """one window (every image seen once) and five windows (images seen by up to three): loop vs stepwise"""
+    a, la = _run_small("0", monkeypatch, cuda_device, niter=12, start_b=12, graph=True, engine="steps", T=T, H=H, W=W)
+    f, lf = _run_small("0", monkeypatch, cuda_device, niter=12, start_b=12, engine="loop", T=T, H=H, W=W)
+    for name in ("im_poses", "im_focals", "pw_poses", "im_depthmaps"):
+        d = float((getattr(a, name).detach() - getattr(f, name).detach()).abs().max())
+        assert d < 2e-4, (name, d)
+    assert abs(la - lf) / la < 1e-3
