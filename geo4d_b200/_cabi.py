@@ -29,6 +29,7 @@ class GemmDesc(C.Structure):
         ("rows_per_bias", C.c_int), ("act", C.c_int),
         ("residual", C.c_void_p), ("ldr", C.c_int64),
         ("tile_n", C.c_int32), ("cta_pair", C.c_int32),
+        ("split_k", C.c_int32), ("reserved_", C.c_int32), ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64),
     ]
 
 
@@ -52,7 +53,7 @@ class AlignLoopDesc(C.Structure):
         ("focal_break", C.c_float),
         ("world", C.c_int), ("rank", C.c_int), ("img_lo", C.c_int * 17), ("rec_doubles", C.c_int),
         ("peer_rec", C.c_void_p * 16), ("peer_flag", C.c_void_p * 16),
-        ("flag_base", C.c_ulonglong),
+        ("flag_base", C.c_ulonglong), ("debug_ns", C.c_void_p),
     ]
 
 

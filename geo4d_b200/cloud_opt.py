@@ -865,6 +865,9 @@ class LightPointCloudGroupOptimizer(nn.Module):
                 d.peer_flag[r] = ex.ptrs[r]
                 d.peer_rec[r] = ex.ptrs[r] + 256
             d.flag_base = sharding.reserve_flags(self._niter_total)
+        if os.environ.get("GEO4D_ALIGN_TRACE", "0") == "1":
+            keep["dbg"] = torch.zeros(8, device=dev, dtype=torch.int64)
+            d.debug_ns = P(keep["dbg"])
         st["loop_desc"] = d
         self._shard = {"world": world, "rank": rank, "img_lo": img_lo, "transport": ex.how if ex else None}
 
@@ -1023,6 +1026,11 @@ class LightPointCloudGroupOptimizer(nn.Module):
         if loop:
             self._gather_depth()
         torch.cuda.synchronize()
+        if loop and "dbg" in st.get("loop_keep", {}):
+            t = st["loop_keep"]["dbg"].cpu().numpy().astype(np.float64)
+            n = max(t[6], 1.0)
+            print("align loop trace (us per iteration, CTA 0): " + ", ".join(
+                f"{k}={t[i] / n * 1e-3:.1f}" for i, k in enumerate(("dense", "barrier1", "fold", "exchange", "small", "barrier2"))))
         if self._profile is not None:
             print("align profile:", ", ".join(f"{n}={t * 1e3:.1f}ms" for n, t in self._profile))
         self._state = st

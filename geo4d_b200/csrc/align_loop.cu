@@ -50,6 +50,7 @@ struct LoopArgs {
   double* peer_rec[LOOP_MAX_RANKS];            // every rank's receive buffer [2][world][rec_doubles] (peer-mapped)
   unsigned long long* peer_flag[LOOP_MAX_RANKS];   // every rank's flag array [world]
   unsigned long long flag_base;                // flags carry flag_base + iteration + 1 (monotonic across calls)
+  unsigned long long* dbg;                     // optional [8] accumulated %globaltimer deltas of CTA 0 (ns)
   SmallArgs small;
 };
 
@@ -127,12 +128,13 @@ __device__ __forceinline__ void dense_unit(const LoopArgs& a, const int n, const
     const float mv[4] = {m4.x, m4.y, m4.z, m4.w};
     const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
     float d[4], xc[4], yc[4], Xw0[4], Xw1[4], Xw2[4], g0[4], g1[4], g2[4], ginv[4], inv[4], du[4], dv[4];
+    int py = p0 / a.W, px = p0 - py * a.W;   // one integer division per quad; the other three pixels follow by increment
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int p = p0 + j;
       d[j] = __expf(ldv[j]);
-      du[j] = (float)(p % a.W) - cx;
-      dv[j] = (float)(p / a.W) - cy;
+      du[j] = (float)px - cx;
+      dv[j] = (float)py - cy;
+      if (++px == a.W) { px = 0; ++py; }
       xc[j] = d[j] * du[j] * invf;
       yc[j] = d[j] * dv[j] * invf;
       Xw0[j] = R[0] * xc[j] + R[1] * yc[j] + R[2] * d[j] + R[3];
@@ -246,7 +248,7 @@ __device__ __forceinline__ void dense_unit(const LoopArgs& a, const int n, const
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(LOOP_THREADS, 1)
+__global__ void __launch_bounds__(LOOP_THREADS, 2)
 align_loop_kernel(const LoopArgs a) {
   extern __shared__ float lsh[];
   float* red = lsh;                                     // [16 warps][PART_STRIDE]
@@ -259,8 +261,13 @@ align_loop_kernel(const LoopArgs a) {
   const int units = n_loc * a.chunks;
   unsigned int gen = ld_acquire_gpu(&a.bar[1]);   // identical in every CTA: the previous launch left it settled
 
+  unsigned long long tk[7];
+  auto stamp = [&](int i) {
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tk[i]));
+  };
   for (int it = a.it0; it < a.it1; ++it) {
     const float* sc = a.scal + (long long)it * 8;
+    stamp(0);
     // ------------------------------------------------------------------ 1. dense part
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       const int n = a.n_lo + u / a.chunks, chunk = u % a.chunks;
@@ -289,7 +296,9 @@ align_loop_kernel(const LoopArgs a) {
       }
     }
     // ------------------------------------------------------------------ 2.
+    stamp(1);
     grid_barrier(a.bar, gen);
+    stamp(2);
     // ------------------------------------------------------------------ 3. fold, exchange, small step
     if (blockIdx.x == 0) {
       const int N = a.N, G = a.G;
@@ -338,6 +347,7 @@ align_loop_kernel(const LoopArgs a) {
         if (i < 12) a.gS[g * 12 + i] = s; else a.gst[g * 2 + (i - 12)] = s;
       }
       __syncthreads();
+      stamp(3);
       if (a.world > 1) {
         // (c) exchange: record = {gpose of my images (max_loc*12) | gS (G*12) | gst (G*2) | scal (3)}
         const int par = it & 1;
@@ -383,12 +393,19 @@ align_loop_kernel(const LoopArgs a) {
         a.gscal[threadIdx.x] = s_tot[threadIdx.x];
       }
       __syncthreads();
+      stamp(4);
       // (d) O(N + G) parameters + refreshed matrices (replicated on every rank from identical totals)
       align_small_body(a.small, it, small_sh);
       __syncthreads();
+      stamp(5);
     }
     // ------------------------------------------------------------------ 4.
     grid_barrier(a.bar, gen);
+    stamp(6);
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) {   // dense | barrier 1 | fold | exchange | small step | barrier 2
+      for (int i = 0; i < 6; ++i) a.dbg[i] += tk[i + 1] - tk[i];
+      a.dbg[6] += 1;
+    }
   }
 }
 
@@ -413,7 +430,7 @@ static size_t loop_smem_bytes(int N, int G, int n_loc, int max_ne) {
 extern "C" int geo4d_align_loop_chunks(int n_images_local, int HW) {
   const int sms = device_sm_count();
   if (sms <= 0 || n_images_local < 1) return 1;
-  int c = sms / n_images_local;   // floor: the units of a rank must not spill into a second wave of CTAs
+  int c = 2 * sms / n_images_local;   // two CTAs per SM; floor: the units of a rank must not spill into a second wave
   const int quads = HW / 4;
   const int maxc = (quads + LOOP_THREADS - 1) / LOOP_THREADS;   // at least one quad per thread and chunk
   if (c > maxc) c = maxc;
@@ -454,6 +471,7 @@ extern "C" int geo4d_align_loop(const g4_align_loop_desc* d, g4_stream_t stream_
   a.world = d->world; a.rank = d->rank;
   a.rec_doubles = d->rec_doubles;
   a.flag_base = d->flag_base;
+  a.dbg = reinterpret_cast<unsigned long long*>(d->debug_ns);
   for (int r = 0; r <= LOOP_MAX_RANKS; ++r) a.img_lo[r] = 0;
   for (int r = 0; r < LOOP_MAX_RANKS; ++r) { a.peer_rec[r] = nullptr; a.peer_flag[r] = nullptr; }
   if (d->world > 1) {

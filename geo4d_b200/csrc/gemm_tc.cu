@@ -41,6 +41,8 @@ struct GemmArgs {
   const void* residual;
   long long ldr;
   int tma_store;              // 1: bf16 tile goes out through shared memory + TMA (tmC valid)
+  int split_k;                // >1: K range split over `split_k` CTAs per output tile, raw fp32 partials to out + ks*split_stride
+  long long split_stride;     // elements between the partial planes
   unsigned long long* trace;  // debug: [grid][16] globaltimer stamps (geo4d_debug_gemm_trace), normally null
 };
 
@@ -125,39 +127,43 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int m_tiles = args.tiles_x * args.tiles_y * args.tiles_n;
   // a pair takes two consecutive row boxes (2*mt2 + rank); an odd tail box is fully out of bounds for the
   // partner: its loads are zero-filled and its stores clipped by the TMA unit
-  const int total_tiles = (TWO ? (m_tiles + 1) / 2 : m_tiles) * args.n_tiles;
+  const int out_tiles = (TWO ? (m_tiles + 1) / 2 : m_tiles) * args.n_tiles;
+  const int total_tiles = out_tiles * args.split_k;   // tile = out_tile * split_k + ks: the parts of one tile run side by side
   const int k_iters = args.num_taps * args.kc_per_tap;
+  const int k_per = (k_iters + args.split_k - 1) / args.split_k;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = unit; tile < total_tiles; tile += n_units) {
-        const int nt = tile % args.n_tiles;
-        const int mt = TWO ? 2 * (tile / args.n_tiles) + rank : tile / args.n_tiles;
+        const int ot = tile / args.split_k, ks = tile - ot * args.split_k;
+        const int nt = ot % args.n_tiles;
+        const int mt = TWO ? 2 * (ot / args.n_tiles) + rank : ot / args.n_tiles;
         const int x0 = (mt % args.tiles_x) * args.box_w;
         const int y0 = ((mt / args.tiles_x) % args.tiles_y) * args.box_h;
         const int n0 = (mt / (args.tiles_x * args.tiles_y)) * args.box_n;
-        for (int tap = 0; tap < args.num_taps; ++tap) {
+        const int k0 = ks * k_per, k1 = min(k0 + k_per, k_iters);
+        int tap = k0 / args.kc_per_tap, kc = k0 - tap * args.kc_per_tap;
+        for (int ki = k0; ki < k1; ++ki) {
           const int dx = args.tap_dx[tap], dy = args.tap_dy[tap];
           const int bz = args.b_batched ? n0 : tap;
-          for (int kc = 0; kc < args.kc_per_tap; ++kc) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
-            uint8_t* sB = sA + Cfg::A_BYTES;
-            if (TWO) {
-              // both CTAs' bytes are counted on the leader's barrier; only the leader arms it
-              if (rank == 0) mbar_expect_tx(&full[stage], 2u * (args.a_box_bytes + Cfg::B_BYTES));
-              const uint32_t lb = leader_bar_addr(&full[stage]);
-              tma_load_4d_2sm(sA, &tmA, lb, kc * 64, x0 + dx, y0 + dy, n0);
-              tma_load_3d_2sm(sB, &tmB, lb, kc * 64, nt * BLOCK_N + rank * (BLOCK_N / 2), bz);
-            } else {
-              mbar_expect_tx(&full[stage], args.a_box_bytes + Cfg::B_BYTES);
-              tma_load_4d(sA, &tmA, &full[stage], kc * 64, x0 + dx, y0 + dy, n0);
-              tma_load_3d(sB, &tmB, &full[stage], kc * 64, nt * BLOCK_N, bz);
-            }
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sB = sA + Cfg::A_BYTES;
+          if (TWO) {
+            // both CTAs' bytes are counted on the leader's barrier; only the leader arms it
+            if (rank == 0) mbar_expect_tx(&full[stage], 2u * (args.a_box_bytes + Cfg::B_BYTES));
+            const uint32_t lb = leader_bar_addr(&full[stage]);
+            tma_load_4d_2sm(sA, &tmA, lb, kc * 64, x0 + dx, y0 + dy, n0);
+            tma_load_3d_2sm(sB, &tmB, lb, kc * 64, nt * BLOCK_N + rank * (BLOCK_N / 2), bz);
+          } else {
+            mbar_expect_tx(&full[stage], args.a_box_bytes + Cfg::B_BYTES);
+            tma_load_4d(sA, &tmA, &full[stage], kc * 64, x0 + dx, y0 + dy, n0);
+            tma_load_3d(sB, &tmB, &full[stage], kc * 64, nt * BLOCK_N, bz);
           }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++kc == args.kc_per_tap) { kc = 0; ++tap; }
         }
       }
     }
@@ -173,7 +179,9 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
-        for (int ki = 0; ki < k_iters; ++ki) {
+        const int ks_m = tile % args.split_k;
+        const int kn = min(k_per, k_iters - ks_m * k_per);
+        for (int ki = 0; ki < kn; ++ki) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           if (it == 0 && ki == 0) trace_stamp(args, 2);
@@ -217,8 +225,9 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int tile = unit; tile < total_tiles; tile += n_units, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int nt = tile % args.n_tiles;
-      const int mt = TWO ? 2 * (tile / args.n_tiles) + rank : tile / args.n_tiles;
+      const int ot = tile / args.split_k, ks = tile - ot * args.split_k;
+      const int nt = ot % args.n_tiles;
+      const int mt = TWO ? 2 * (ot / args.n_tiles) + rank : ot / args.n_tiles;
       const int x0 = (mt % args.tiles_x) * args.box_w;
       const int y0 = ((mt / args.tiles_x) % args.tiles_y) * args.box_h;
       const int n0 = (mt / (args.tiles_x * args.tiles_y)) * args.box_n;
@@ -405,7 +414,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           ++kk;
         } else if (row_ok) {
           if (args.out_fp32) {
-            float* op = reinterpret_cast<float*>(args.out) + row * args.ldc + scol0;
+            float* op = reinterpret_cast<float*>(args.out) + (long long)ks * args.split_stride + row * args.ldc + scol0;
             if (vec_ok && ((reinterpret_cast<uintptr_t>(op) & 31) == 0)) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -465,6 +474,67 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
+
+// Second pass of a split-K tap-GEMM: out = epilogue(sum over the `split` fp32 partial planes, in plane order).
+// Same epilogue terms as the fused path (alpha, bias, per-frame row bias, SiLU, residual); 8 columns per thread.
+struct ReduceArgs {
+  const float* ws; long long plane; int split;
+  long long M; int n_out;
+  void* out; long long ldc; int out_fp32;
+  float alpha; const float* bias; const float* row_bias; long long row_bias_ld; int rows_per_bias; int act;
+  const void* residual; long long ldr;
+};
+
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const ReduceArgs a) {
+  const int groups = (a.n_out + 7) >> 3;
+  const long long total = a.M * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / groups;
+    const int c0 = (int)(i - row * groups) << 3;
+    const int nc = min(8, a.n_out - c0);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float* src = a.ws + row * a.n_out + c0;
+    const bool vec = (nc == 8) && ((a.n_out & 3) == 0);
+    for (int s = 0; s < a.split; ++s) {
+      const float* p = src + (long long)s * a.plane;
+      if (vec) {
+        const float4 u = __ldcg(reinterpret_cast<const float4*>(p)), v = __ldcg(reinterpret_cast<const float4*>(p + 4));
+        acc[0] += u.x; acc[1] += u.y; acc[2] += u.z; acc[3] += u.w;
+        acc[4] += v.x; acc[5] += v.y; acc[6] += v.z; acc[7] += v.w;
+      } else {
+        for (int j = 0; j < nc; ++j) acc[j] += __ldcg(p + j);
+      }
+    }
+    const float* rb = a.row_bias ? a.row_bias + (row / a.rows_per_bias) * a.row_bias_ld + c0 : nullptr;
+    const __nv_bfloat16* rr = a.residual ? reinterpret_cast<const __nv_bfloat16*>(a.residual) + row * a.ldr + c0 : nullptr;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < nc) {
+        float o = fmaf(acc[j], a.alpha, a.bias ? __ldg(a.bias + c0 + j) : 0.f);
+        if (rb) o += __ldg(rb + j);
+        if (a.act == G4_ACT_SILU) o = silu_f(o);
+        if (rr) o += __bfloat162float(rr[j]);
+        acc[j] = o;
+      }
+    }
+    if (a.out_fp32) {
+      float* op = reinterpret_cast<float*>(a.out) + row * a.ldc + c0;
+      for (int j = 0; j < nc; ++j) op[j] = acc[j];
+    } else {
+      __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + row * a.ldc + c0;
+      if (nc == 8 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+        uint4 w;
+        w.x = pack_bf16x2(acc[0], acc[1]); w.y = pack_bf16x2(acc[2], acc[3]);
+        w.z = pack_bf16x2(acc[4], acc[5]); w.w = pack_bf16x2(acc[6], acc[7]);
+        *reinterpret_cast<uint4*>(op) = w;
+      } else {
+        for (int j = 0; j < nc; ++j) op[j] = __float2bfloat16(acc[j]);
+      }
+    }
+  }
+}
+
 template <int BLOCK_N, bool TWO>
 static int launch_tap_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                            const GemmArgs& a, int num_sms, cudaStream_t stream) {
@@ -486,7 +556,7 @@ static int launch_tap_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const
     const int total = ((m_tiles + 1) / 2) * a.n_tiles, pairs = num_sms / 2;
     grid = 2 * (total < pairs ? total : pairs);
   } else {
-    const int total = m_tiles * a.n_tiles;
+    const int total = m_tiles * a.n_tiles * a.split_k;
     grid = total < num_sms ? total : num_sms;
   }
   cudaError_t e = launch_ex(tap_gemm_kernel<BLOCK_N, TWO>, dim3(grid), dim3(320), Cfg::SMEM_BYTES, stream, TWO ? 2 : 1,
@@ -584,12 +654,44 @@ extern "C" int geo4d_tap_gemm(const g4_gemm_desc* d, g4_stream_t stream_) {
     }
   }
 
+  // Split-K: layers with few output tiles and a long reduction (the 5x8 level: 640 rows, K up to 23 040) leave most
+  // SMs idle.  The K range is cut into `split` parts that run side by side; each CTA stores its raw fp32 accumulator
+  // into a plane of the caller's workspace and splitk_reduce_kernel adds the planes IN ORDER and applies the epilogue
+  // (deterministic; no atomics).  d->split_k: 0 = decide here, 1 = never, n = exactly n parts.
+  int split = 1;
+  {
+    const long long m_tiles_s = (long long)((d->W + d->box_w - 1) / d->box_w) * ((d->H + d->box_h - 1) / d->box_h) *
+                                ((d->N + d->box_n - 1) / d->box_n);
+    const long long out_tiles = m_tiles_s * ((n + bn - 1) / bn);
+    const long long k_it = (long long)d->num_taps * (d->K / 64);
+    const long long rows_total = (long long)d->W * d->H * d->N;
+    const bool can = !two && !d->b_batched && d->act != G4_ACT_GEGLU && d->workspace != nullptr;
+    if (d->split_k < 0 || d->split_k > 64) { set_last_error("tap_gemm: split_k=%d", d->split_k); return G4_ERR_BAD_ARG; }
+    if (d->split_k > 1) {
+      if (!can) { set_last_error("tap_gemm: split_k needs a workspace, a single-CTA tile, no GEGLU and no batched B"); return G4_ERR_BAD_ARG; }
+      split = d->split_k;
+    } else if (d->split_k == 0 && can && out_tiles * 2 <= sms && k_it >= 16) {
+      split = (int)(sms / out_tiles);
+      if (split > k_it / 8) split = (int)(k_it / 8);       // at least 8 k-steps per part
+      if (split > 16) split = 16;
+    }
+    if (split > 1) {
+      const long long k_per = (k_it + split - 1) / split;
+      split = (int)((k_it + k_per - 1) / k_per);            // no empty part
+      if ((unsigned long long)split * rows_total * n * sizeof(float) > d->workspace_bytes) {
+        if (d->split_k > 1) { set_last_error("tap_gemm: split_k=%d needs %lld workspace bytes", split, (long long)split * rows_total * n * 4); return G4_ERR_WORKSPACE; }
+        split = 1;
+      }
+    }
+    if (split < 1) split = 1;
+  }
+
   CUtensorMap tmA, tmB, tmC;
   memset(&tmC, 0, sizeof(tmC));
   // bf16 outputs with a 16-byte aligned base and row pitch leave through TMA stores (tile-shaped box, 32 columns)
   const int n_store = d->act == G4_ACT_GEGLU ? d->n_out / 2 : d->n_out;
   const bool tma_store = !d->out_fp32 && (d->ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) &&
-                         n_store >= 32 && !g_no_tma_store;
+                         n_store >= 32 && !g_no_tma_store && split == 1;
   if (tma_store) {
     uint64_t dims[4] = {(uint64_t)n_store, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
     uint64_t strides[3] = {(uint64_t)d->ldc * 2, (uint64_t)d->ldc * 2 * (uint64_t)d->W,
@@ -634,21 +736,41 @@ extern "C" int geo4d_tap_gemm(const g4_gemm_desc* d, g4_stream_t stream_) {
   a.act = d->act; a.residual = d->residual; a.ldr = d->ldr;
   a.trace = g_gemm_trace;
   a.tma_store = tma_store ? 1 : 0;
+  a.split_k = split;
+  a.split_stride = 0;
+  ReduceArgs ra;
+  if (split > 1) {   // partial mode: raw fp32 accumulators into the workspace planes, epilogue in the reduce pass
+    const long long rows_total = (long long)d->W * d->H * d->N;
+    ra.ws = reinterpret_cast<const float*>(d->workspace); ra.plane = rows_total * n; ra.split = split;
+    ra.M = rows_total; ra.n_out = n; ra.out = d->out; ra.ldc = d->ldc; ra.out_fp32 = d->out_fp32;
+    ra.alpha = d->alpha; ra.bias = d->bias; ra.row_bias = d->row_bias; ra.row_bias_ld = d->row_bias_ld;
+    ra.rows_per_bias = a.rows_per_bias; ra.act = d->act; ra.residual = d->residual; ra.ldr = d->ldr;
+    a.out = d->workspace; a.ldc = n; a.out_fp32 = 1; a.alpha = 1.0f; a.bias = nullptr; a.row_bias = nullptr;
+    a.act = G4_ACT_NONE; a.residual = nullptr; a.split_stride = ra.plane;
+  }
 
+  int rc;
   if (two) {
     switch (bn) {
-      case 32: return launch_tap_gemm<32, true>(tmA, tmB, tmC, a, sms, stream);
-      case 64: return launch_tap_gemm<64, true>(tmA, tmB, tmC, a, sms, stream);
-      case 128: return launch_tap_gemm<128, true>(tmA, tmB, tmC, a, sms, stream);
-      case 160: return launch_tap_gemm<160, true>(tmA, tmB, tmC, a, sms, stream);
-      default: return launch_tap_gemm<256, true>(tmA, tmB, tmC, a, sms, stream);
+      case 32: rc = launch_tap_gemm<32, true>(tmA, tmB, tmC, a, sms, stream); break;
+      case 64: rc = launch_tap_gemm<64, true>(tmA, tmB, tmC, a, sms, stream); break;
+      case 128: rc = launch_tap_gemm<128, true>(tmA, tmB, tmC, a, sms, stream); break;
+      case 160: rc = launch_tap_gemm<160, true>(tmA, tmB, tmC, a, sms, stream); break;
+      default: rc = launch_tap_gemm<256, true>(tmA, tmB, tmC, a, sms, stream); break;
+    }
+  } else {
+    switch (bn) {
+      case 32: rc = launch_tap_gemm<32, false>(tmA, tmB, tmC, a, sms, stream); break;
+      case 64: rc = launch_tap_gemm<64, false>(tmA, tmB, tmC, a, sms, stream); break;
+      case 128: rc = launch_tap_gemm<128, false>(tmA, tmB, tmC, a, sms, stream); break;
+      case 160: rc = launch_tap_gemm<160, false>(tmA, tmB, tmC, a, sms, stream); break;
+      default: rc = launch_tap_gemm<256, false>(tmA, tmB, tmC, a, sms, stream); break;
     }
   }
-  switch (bn) {
-    case 32: return launch_tap_gemm<32, false>(tmA, tmB, tmC, a, sms, stream);
-    case 64: return launch_tap_gemm<64, false>(tmA, tmB, tmC, a, sms, stream);
-    case 128: return launch_tap_gemm<128, false>(tmA, tmB, tmC, a, sms, stream);
-    case 160: return launch_tap_gemm<160, false>(tmA, tmB, tmC, a, sms, stream);
-    default: return launch_tap_gemm<256, false>(tmA, tmB, tmC, a, sms, stream);
-  }
+  if (rc != G4_OK || split == 1) return rc;
+  const long long work = ra.M * ((ra.n_out + 7) / 8);
+  long long blocks = (work + 255) / 256;
+  if (blocks > 4ll * sms) blocks = 4ll * sms;
+  launch_pdl(splitk_reduce_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, ra);
+  return check_launch("tap_gemm split-K reduce");
 }

@@ -37,7 +37,8 @@ class capture_graph:
         self.graph = graph
 
     def __enter__(self):
-        self.graph.capture_begin()
+        # thread_local: calls made by OTHER threads (NCCL's watchdog, the clock sampler) cannot invalidate the capture
+        self.graph.capture_begin(capture_error_mode="thread_local")
         return self.graph
 
     def __exit__(self, exc_type, exc, tb):
@@ -95,8 +96,11 @@ def tap_gemm(a: torch.Tensor, K: int, W: int, H: int, N: int, strides: Tuple[int
     d.act = act
     d.residual = _ptr(residual)
     d.ldr = ldr
+    ws = _splitk_workspace(a.device)
+    d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel() * 4
     if _FORCE_TILE is not None:
         d.tile_n, d.cta_pair = _FORCE_TILE
+        d.split_k = 1 if _FORCE_SPLIT is None else _FORCE_SPLIT   # bitwise-equality tests keep the k-step order fixed
     elif _AUTOTUNE:
         key = (K, W, H, N, bw, bh, bn, len(taps), n_out, int(b_batched), d.out_fp32, act, bias is not None,
                row_bias is not None, residual is not None)
@@ -104,7 +108,7 @@ def tap_gemm(a: torch.Tensor, K: int, W: int, H: int, N: int, strides: Tuple[int
         if cfg is None and not torch.cuda.is_current_stream_capturing():
             cfg = _autotune(d, key, out, residual)
         if cfg is not None:
-            d.tile_n, d.cta_pair = cfg
+            d.tile_n, d.cta_pair, d.split_k = cfg
     rc = lib().geo4d_tap_gemm(C.byref(d), C.c_void_p(_stream()))
     if rc != 0 and _FORCE_TILE is not None:    # a forced configuration that is not legal for this shape: library's choice
         d.tile_n, d.cta_pair = 0, 0
@@ -120,9 +124,24 @@ def tap_gemm(a: torch.Tensor, K: int, W: int, H: int, N: int, strides: Tuple[int
 # small CUDA graph (GPU-bound, no launch gaps) and the winner is pinned for the rest of the process.
 # GEO4D_AUTOTUNE=0 leaves the choice to the library's cost model.
 _AUTOTUNE = os.environ.get("GEO4D_AUTOTUNE", "1") != "0"
+_SPLITK = os.environ.get("GEO4D_SPLITK", "1") != "0"
+_splitk_ws: dict = {}
+
+
+def _splitk_workspace(device) -> torch.Tensor:
+    """Caller-owned scratch for the partial planes of split-K tap-GEMMs (only small-M layers split: 64 MiB holds
+    16 planes of a 640 x 1280 fp32 tile set with room to spare).  One buffer per device; launches on one stream
+    are ordered, so consecutive GEMMs can share it."""
+    ws = _splitk_ws.get(device)
+    if ws is None:
+        ws = torch.empty(16 << 20, device=device, dtype=torch.float32)
+        _splitk_ws[device] = ws
+    return ws
 _TUNED: dict = {}
 _TUNE_LOG: list = []
+_TUNE_ERRORS: list = []   # configurations the library refused during tuning (visible, not swallowed)
 _FORCE_TILE: Optional[Tuple[int, int]] = None   # (tile_n, cta_pair) for every launch; tests and experiments only
+_FORCE_SPLIT: Optional[int] = None              # with _FORCE_TILE: number of K parts (tests)
 
 
 def tuned_configs():
@@ -147,9 +166,17 @@ def _autotune(d: GemmDesc, key, out: torch.Tensor, residual: Optional[torch.Tens
     side = torch.cuda.Stream()
     results = {}
     n_rep = 6
-    for pair in (1, 2):
-        for tn in (256, 160, 128, 64, 32):
-            t.tile_n, t.cta_pair = tn, pair
+    cands = [(tn, pair, 1) for pair in (1, 2) for tn in (256, 160, 128, 64, 32)]
+    if _SPLITK and not d.b_batched and d.act != ACT_GEGLU:
+        # split-K candidates only where the library would actually split: few output tiles, long reduction
+        m_tiles = -(-d.W // d.box_w) * -(-d.H // d.box_h) * -(-d.N // d.box_n)
+        k_iters = d.num_taps * (d.K // 64)
+        for tn in (256, 160, 128, 64):
+            if m_tiles * -(-d.n_out // tn) * 2 <= 148 and k_iters >= 16:
+                cands.append((tn, 1, 0))   # 0: the library picks the number of K parts
+    for tn, pair, sk in cands:
+        if True:
+            t.tile_n, t.cta_pair, t.split_k = tn, pair, sk
             side.wait_stream(cur)
             with torch.cuda.stream(side):
                 if L.geo4d_tap_gemm(C.byref(t), C.c_void_p(side.cuda_stream)) != 0:
@@ -169,19 +196,20 @@ def _autotune(d: GemmDesc, key, out: torch.Tensor, residual: Optional[torch.Tens
                         e1.synchronize()
                         us = e0.elapsed_time(e1) * 1e3 / n_rep
                         best = us if best is None else min(best, us)
-                    results[(tn, pair)] = best
+                    results[(tn, pair, sk)] = best
                     del g
-                except Exception:   # a configuration that cannot be captured is simply not a candidate
+                except _cabi.Geo4DError as ex:   # the library refused this configuration for this shape
+                    _TUNE_ERRORS.append((key, (tn, pair, sk), str(ex)))
                     continue
     cur.wait_stream(side)
     if not results:
-        _TUNED[key] = (0, 0)
-        return (0, 0)
+        _TUNED[key] = (0, 0, 1)
+        return (0, 0, 1)
     cfg = min(results, key=results.get)
     _TUNED[key] = cfg
     _TUNE_LOG.append((key, cfg, results))
     if os.environ.get("GEO4D_AUTOTUNE_VERBOSE") == "1":
-        print(f"[geo4d autotune] {key} -> tile_n={cfg[0]} {'pair' if cfg[1] == 2 else 'single'} "
+        print(f"[geo4d autotune] {key} -> tile_n={cfg[0]} {'pair' if cfg[1] == 2 else 'single'}{' split-K' if cfg[2] == 0 else ''} "
               f"{results[cfg]:.1f} us  (all: {dict((k, round(v, 1)) for k, v in sorted(results.items()))})", flush=True)
     return cfg
 

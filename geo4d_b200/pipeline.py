@@ -17,7 +17,7 @@ import torch
 
 from . import ops
 from .cloud_opt import LightPointCloudGroupOptimizer
-from .sampler import DDIMSampler
+from .sampler import DDIMSampler, DDIMSampler_multicond
 
 POSTPROCESS_DEFAULTS = dict(not_shared_focal=False, use_gt_focal=False, flow_loss_weight=0.0, flow_loss_fn="l1",
                             depth_regularize_weight=0.0, n_iter=500, temporal_smoothing_weight=0.015,
@@ -58,7 +58,8 @@ def raymap_to_camera_matrix(raymap: torch.Tensor, crossmap: torch.Tensor) -> tor
 class Geo4DPipeline:
     def __init__(self, model, pointmap_vae=None, ddim_steps: int = 50, ddim_eta: float = 0.0,
                  unconditional_guidance_scale: float = 1.0, timestep_spacing: str = "uniform_trailing",
-                 guidance_rescale: float = 0.0, postprocess: Optional[dict] = None, seed: int = 123):
+                 guidance_rescale: float = 0.0, postprocess: Optional[dict] = None, seed: int = 123,
+                 multiple_cond_cfg: bool = False, cfg_img: Optional[float] = None):
         self.model = model
         self.pointmap_vae = pointmap_vae
         self.ddim_steps = ddim_steps
@@ -69,7 +70,9 @@ class Geo4DPipeline:
         self.post = dict(POSTPROCESS_DEFAULTS)
         self.post.update(postprocess or {})
         self.seed = seed
-        self.sampler = DDIMSampler(model)
+        self.multiple_cond_cfg = multiple_cond_cfg      # infer_geo4d.py:119 (DDIMSampler_multicond) / :188-194
+        self.cfg_img = cfg_img
+        self.sampler = DDIMSampler_multicond(model) if multiple_cond_cfg else DDIMSampler(model)
         self.timings: Dict[str, float] = {}
         self.events: List = []
 
@@ -117,18 +120,32 @@ class Geo4DPipeline:
         if m.model.conditioning_key == "hybrid":
             with self.phase("encode"):
                 cond["c_concat"] = [m.encode_first_stage(videos, noise=z_noise)]
-        uc = None
+        uc, uc_2 = None, None
         if self.cfg_scale != 1.0:
-            uc = {"c_crossattn": [torch.cat([cond_emb, img_emb], dim=1)]}  # uncond_type 'empty_seq' with prompt ""
+            # infer_geo4d.py:168-187: uncond_type 'empty_seq' re-embeds the prompt "" and the image branch embeds an
+            # all-zero image again -- with text_input off and cross_attention off these are the SAME tensors as the
+            # conditional ones; the sampler recognises identical conditionings and evaluates the U-Net once
+            if m.uncond_type == "empty_seq":
+                uc_emb = m.get_learned_conditioning([""] * b)
+            elif m.uncond_type == "zero_embed":
+                uc_emb = torch.zeros_like(cond_emb)
+            else:
+                raise NotImplementedError(f"uncond_type {m.uncond_type!r}")
+            uc = {"c_crossattn": [torch.cat([uc_emb, img_emb], dim=1)]}
             if "c_concat" in cond:
                 uc["c_concat"] = cond["c_concat"]
+            if self.multiple_cond_cfg and self.cfg_img != 1.0:      # :188-194: image yes, text ""
+                uc_2 = {"c_crossattn": [torch.cat([uc_emb, img_emb], dim=1)]}
+                if "c_concat" in cond:
+                    uc_2["c_concat"] = cond["c_concat"]
         with self.phase("ddim"):
             samples, _ = self.sampler.sample(S=self.ddim_steps, conditioning=cond, batch_size=b,
                                              shape=noise_shape[1:], verbose=False,
                                              unconditional_guidance_scale=self.cfg_scale,
                                              unconditional_conditioning=uc, eta=self.ddim_eta, mask=None, x0=None,
                                              x_T=x_T, fs=fs_t, timestep_spacing=self.timestep_spacing,
-                                             guidance_rescale=self.guidance_rescale)
+                                             guidance_rescale=self.guidance_rescale, cfg_img=self.cfg_img,
+                                             unconditional_conditioning_img_nonetext=uc_2)
         with self.phase("decode"):
             out = self.decode_latents(samples).unsqueeze(1)
         return out
@@ -181,13 +198,14 @@ class Geo4DPipeline:
 
     @torch.no_grad()
     def reconstruct(self, videos_all: torch.Tensor, stride: int = 8, windows: Optional[List[slice]] = None,
-                    x_T_fn=None, z_noise_fn=None, align: bool = True):
+                    x_T_fn=None, z_noise_fn=None, align: bool = True, keep_images: bool = False):
         """videos_all [1, 3, T, H, W] -> (scene, pred_list).  x_T(w) = randn(seed + w) unless x_T_fn is given
         (per-window seeds make window sharding reproducible)."""
         B, C, T, H, W = videos_all.shape
         assert B == 1, "only support batch size = 1 (infer_geo4d.py:355)"
         dev = videos_all.device
         windows = windows if windows is not None else sliding_windows(T, stride)
+        self.last_windows = windows
         h, w = H // 8, W // 8
         ch = self.model.model.diffusion_model.out_channels
         pred_list, view_list = [], []
@@ -205,7 +223,10 @@ class Geo4DPipeline:
             vslice = valid[sl].contiguous()
             pred_list.append(self.window_predictions(maps[:, 0], vslice))
             valid[sl] = vslice
-            view_list.append([{"idx": (i,)} for i in range(sl.start, sl.stop)])
+            if keep_images:   # the reference's views carry the frames (save_rgb_imgs); costs a device -> host copy each
+                view_list.append([{"img": videos_all[0, :, i], "idx": (i,)} for i in range(sl.start, sl.stop)])
+            else:
+                view_list.append([{"idx": (i,)} for i in range(sl.start, sl.stop)])
         torch.cuda.synchronize()
         self.timings["diffusion_s"] = time.time() - t0
         scene = None

@@ -56,6 +56,8 @@ class DDIMSampler(object):
                                              m.sqrt_one_minus_alphas_cumprod.detach().cpu().numpy())
 
     # ------------------------------------------------------------------ public API
+    multicond = False   # DDIMSampler_multicond: 3-way guidance of ddim_multiplecond.py:226-236
+
     @torch.no_grad()
     def sample(self, S, batch_size, shape, conditioning=None, callback=None, normals_sequence=None,
                img_callback=None, quantize_x0=False, eta=0., mask=None, x0=None, temperature=1.,
@@ -68,8 +70,10 @@ class DDIMSampler(object):
             cbs = (c0[0] if isinstance(c0, (list, tuple)) else c0).shape[0]
             if cbs != batch_size:
                 print(f"Warning: Got {cbs} conditionings but batch-size is {batch_size}")
-        # the evaluation script forwards inert extras (cfg_img=None, unconditional_conditioning_img_nonetext=None,
-        # infer_geo4d.py:188-226) that the reference U-Net swallows in **kwargs
+        # guidance extras of the evaluation script (infer_geo4d.py:188-226): the multi-condition sampler consumes
+        # them (ddim_multiplecond.py:214-236), the plain sampler forwards them to a U-Net that swallows them
+        cfg_img = kwargs.pop("cfg_img", None)
+        uc_img = kwargs.pop("unconditional_conditioning_img_nonetext", None)
         kwargs = {k: v for k, v in kwargs.items() if v is not None}
         self.make_schedule(ddim_num_steps=S, ddim_discretize=timestep_spacing, ddim_eta=eta, verbose=schedule_verbose)
         if len(shape) == 3:
@@ -79,52 +83,105 @@ class DDIMSampler(object):
             size = (batch_size, C, T, H, W)
         device = self.model.betas.device
         img = torch.randn(size, device=device) if x_T is None else x_T.to(device)
-        no_cfg = unconditional_conditioning is None or unconditional_guidance_scale == 1.
-        graph_ok = (self.use_cuda_graph and no_cfg and eta == 0. and mask is None and len(size) == 5
-                    and self.model.parameterization == "v" and isinstance(conditioning, dict)
+        # guidance plan: conditionings to evaluate and how to mix their outputs
+        #   plain : v = v_c
+        #   cfg   : v = v_u + s (v_c - v_u)                                   (ddim.py:216-229)
+        #   multi : v = v_u + s_img (v_ui - v_u) + s (v_c - v_ui)              (ddim_multiplecond.py:226-236)
+        guided = unconditional_conditioning is not None and unconditional_guidance_scale != 1.
+        conds, plan = [conditioning], ("plain",)
+        if guided and self.multicond:
+            if uc_img is None:
+                raise ValueError("DDIMSampler_multicond needs unconditional_conditioning_img_nonetext "
+                                 "(infer_geo4d.py:188-194: pass cfg_img != 1)")
+            conds = [conditioning, unconditional_conditioning, uc_img]
+            plan = ("multi", float(unconditional_guidance_scale),
+                    float(unconditional_guidance_scale if cfg_img is None else cfg_img), float(guidance_rescale))
+        elif guided:
+            conds = [conditioning, unconditional_conditioning]
+            plan = ("cfg", float(unconditional_guidance_scale), float(guidance_rescale))
+        graph_ok = (self.use_cuda_graph and mask is None and len(size) == 5 and noise_dropout == 0.
+                    and self.model.parameterization == "v" and all(isinstance(c, dict) for c in conds)
                     and self.model.model.conditioning_key == "hybrid" and score_corrector is None
                     and not quantize_x0 and callback is None and img_callback is None and not kwargs)
         if graph_ok:
-            return self._sample_graph(img, conditioning, fs, log_every_t)
+            return self._sample_graph(img, conds, plan, fs, log_every_t, eta, temperature)
+        if plan[0] == "multi":
+            raise NotImplementedError("3-way guidance is implemented on the CUDA-graph path only")
         return self._sample_eager(img, conditioning, fs, log_every_t, unconditional_guidance_scale,
                                   unconditional_conditioning, guidance_rescale, temperature, noise_dropout,
                                   mask, x0, callback, img_callback, **kwargs)
 
     # ------------------------------------------------------------------ graph path
-    def _sample_graph(self, x_T, cond, fs, log_every_t):
+    @staticmethod
+    def _mix(v, b, which, plan):
+        """guidance mix of the per-conditioning U-Net outputs v [P*b, ...]; which[i] = slot of conditioning i"""
+        if plan[0] == "plain" or len(set(which)) == 1:
+            # identical conditionings give bit-identical outputs, for which every mix above returns v_c exactly
+            return v[which[0] * b:(which[0] + 1) * b]
+        e = [v[w * b:(w + 1) * b] for w in which]
+        if plan[0] == "cfg":
+            out = e[1] + plan[1] * (e[0] - e[1])
+            rescale = plan[2]
+        else:
+            out = e[1] + plan[2] * (e[2] - e[1]) + plan[1] * (e[0] - e[2])
+            rescale = plan[3]
+        if rescale > 0.0:
+            out = rescale_noise_cfg(out, e[0], rescale)
+        return out.contiguous()
+
+    def _sample_graph(self, x_T, conds, plan, fs, log_every_t, eta=0.0, temperature=1.0):
         m = self.model
         unet = m.model.diffusion_model
         S = len(self.ddim_timesteps)
         b, C, T, H, W = x_T.shape
         dev = x_T.device
-        cc = cond["c_crossattn"]
-        cc = cc[0] if len(cc) == 1 else torch.cat(cc, 1)
-        zc = cond["c_concat"]
-        zc = (zc[0] if len(zc) == 1 else torch.cat(zc, 1)).float().contiguous()
+        # unique conditionings (the shipped settings make the "unconditional" one identical to the conditional one:
+        # empty prompt, zero image -- infer_geo4d.py:140-187 -- so guidance then costs ONE U-Net pass, not two)
+        uniq, which = [], []
+        for c in conds:
+            cc = c["c_crossattn"]
+            cc = cc[0] if len(cc) == 1 else torch.cat(cc, 1)
+            zc = c["c_concat"]
+            zc = (zc[0] if len(zc) == 1 else torch.cat(zc, 1)).float().contiguous()
+            for j, (cc_j, zc_j) in enumerate(uniq):
+                if cc_j.shape == cc.shape and zc_j.shape == zc.shape and torch.equal(cc_j, cc) and torch.equal(zc_j, zc):
+                    which.append(j)
+                    break
+            else:
+                which.append(len(uniq))
+                uniq.append((cc, zc))
+        P = len(uniq)
+        cc_all = uniq[0][0] if P == 1 else torch.cat([u[0] for u in uniq], 0)
+        zc_all = uniq[0][1] if P == 1 else torch.cat([u[1] for u in uniq], 0)
         if unet._packed is None:
             unet.prepare()
-        unet.set_context(cc, T)
-        # per-step ResBlock embedding rows for all S steps at once: [S, b * sum(Cout)]
+        unet.set_context(cc_all, T)
+        # per-step ResBlock embedding rows for all S steps at once: [S, P*b * sum(Cout)]
         steps = np.flip(self.ddim_timesteps).copy()
-        ts_all = torch.as_tensor(np.repeat(steps, b), device=dev, dtype=torch.long)
-        fs_all = None if fs is None else fs.to(dev).repeat(S)
-        emb_table = unet.embed(ts_all, fs_all, S * b).reshape(S, -1).contiguous()
-        key = (b, C, T, H, W, zc.shape[1], dev.index)
+        ts_all = torch.as_tensor(np.repeat(steps, P * b), device=dev, dtype=torch.long)
+        fs_all = None if fs is None else fs.to(dev).repeat(S * P)
+        emb_table = unet.embed(ts_all, fs_all, S * P * b).reshape(S, -1).contiguous()
+        stochastic = bool(np.any(np.asarray(self.ddim_sigmas) != 0.0))
+        key = (b, C, T, H, W, zc_all.shape[1], dev.index, P, tuple(which), plan, stochastic,
+               unet._ctx_cache["sig"], id(unet._ctx_cache["kv"]))
         st = self._graphs.get(key)
         if st is None:
             st = {
                 "x": torch.empty((b, C, T, H, W), device=dev, dtype=torch.float32),
-                "zc": torch.empty_like(zc),
-                "emb": torch.empty((b, emb_table.shape[1] // b), device=dev, dtype=torch.float32),
+                "xP": torch.empty((P * b, C, T, H, W), device=dev, dtype=torch.float32) if P > 1 else None,
+                "zc": torch.empty_like(zc_all),
+                "emb": torch.empty((P * b, emb_table.shape[1] // (P * b)), device=dev, dtype=torch.float32),
                 "pred_x0": torch.empty((b, C, T, H, W), device=dev, dtype=torch.float32),
                 "idx": torch.zeros(1, device=dev, dtype=torch.int32),
                 "coef": torch.empty((1024, 6), device=dev, dtype=torch.float32),
+                "noise": torch.empty((b, C, T, H, W), device=dev, dtype=torch.float32) if stochastic else None,
+                "noise_table": None,
                 "emb_table": None,
                 "graph": None,
             }
             self._graphs[key] = st
         st["x"].copy_(x_T)
-        st["zc"].copy_(zc)
+        st["zc"].copy_(zc_all)
         st["coef"][:S].copy_(torch.as_tensor(self.step_coef, device=dev))
         st["idx"].zero_()
         if st["emb_table"] is None or st["emb_table"].shape != emb_table.shape:
@@ -132,14 +189,31 @@ class DDIMSampler(object):
             st["graph"] = None  # table pointer is baked into the graph
         else:
             st["emb_table"].copy_(emb_table)
+        if stochastic:
+            # the reference draws sigma_t * randn per step from the global CUDA generator (ddim.py:273-277); the same
+            # S draws in the same order, made up front so that the captured step only gathers row `idx`
+            noise = torch.stack([torch.randn((b, C, T, H, W), device=dev) for _ in range(S)]).reshape(S, -1)
+            if temperature != 1.:
+                noise = noise * temperature
+            if st["noise_table"] is None or st["noise_table"].shape != noise.shape:
+                st["noise_table"] = noise.contiguous()
+                st["graph"] = None
+            else:
+                st["noise_table"].copy_(noise)
         cin_pad = -(-unet.in_channels // 64) * 64
 
         def one_step():
             ops.gather_row(st["emb_table"], st["idx"], st["emb"])
-            rows = ops.bcthw_to_rows(st["x"], st["zc"], cin_pad)
-            v_rows = unet.forward_rows(rows, st["emb"], (b, T, H, W))
-            v = ops.rows_to_bcthw(v_rows, C, b, T, H, W)
-            ops.ddim_step(st["x"], v, st["coef"], st["idx"], pred_x0=st["pred_x0"])
+            xin = st["x"]
+            if P > 1:
+                st["xP"].view(P, b, C, T, H, W).copy_(st["x"].unsqueeze(0))
+                xin = st["xP"]
+            rows = ops.bcthw_to_rows(xin, st["zc"], cin_pad)
+            v_rows = unet.forward_rows(rows, st["emb"], (P * b, T, H, W))
+            v = self._mix(ops.rows_to_bcthw(v_rows, C, P * b, T, H, W), b, which, plan)
+            if stochastic:
+                ops.gather_row(st["noise_table"], st["idx"], st["noise"])
+            ops.ddim_step(st["x"], v, st["coef"], st["idx"], pred_x0=st["pred_x0"], noise=st["noise"])
             ops.advance_counter(st["idx"], 1)
 
         inter = {"x_inter": [x_T], "pred_x0": [x_T]}
@@ -218,3 +292,9 @@ class DDIMSampler(object):
                 inter["x_inter"].append(img.clone())
                 inter["pred_x0"].append(pred_x0.clone())
         return img, inter
+
+
+class DDIMSampler_multicond(DDIMSampler):
+    """lvdm/models/samplers/ddim_multiplecond.py: text + image guidance with three U-Net evaluations per step
+    (conditional, unconditional, image-only), batched into one pass of the captured step."""
+    multicond = True

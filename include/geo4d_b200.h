@@ -32,7 +32,7 @@ extern "C" {
 
 typedef void* g4_stream_t; /* cudaStream_t */
 
-#define GEO4D_ABI_VERSION 2
+#define GEO4D_ABI_VERSION 3
 
 int geo4d_abi_version(void);
 const char* geo4d_last_error(void);
@@ -99,6 +99,15 @@ typedef struct {
    * configurations of a shape once and pin the fastest (geo4d_b200/ops.py: autotune). */
   int32_t tile_n;            /* 0 | 32 | 64 | 128 | 160 | 256 output columns per tile */
   int32_t cta_pair;          /* 0 auto | 1 single CTA (cta_group::1) | 2 CTA pair (cta_group::2, 256-row tiles) */
+  /* Split-K (ABI v3): layers with few output tiles and a long reduction (5x8 latents, K up to 23 040) run their K
+   * range in `split_k` parts side by side; partial fp32 tiles go to `workspace` and a second kernel adds them in
+   * order and applies the epilogue (deterministic).  0 = library decides, 1 = never, n = n parts.  The workspace is
+   * caller-owned scratch of at least split * rows * n_out * 4 bytes; NULL disables splitting.  The result is
+   * independent of tile_n / cta_pair but (summation order) not of split_k. */
+  int32_t split_k;
+  int32_t reserved_;
+  void* workspace;
+  uint64_t workspace_bytes;
 } g4_gemm_desc;
 
 int geo4d_tap_gemm(const g4_gemm_desc* d, g4_stream_t stream);
@@ -260,6 +269,7 @@ typedef struct g4_align_loop_desc {
   int rec_doubles;                                  /* geo4d_align_loop_record_doubles(max images per rank, G) */
   void* peer_rec[16]; void* peer_flag[16];
   unsigned long long flag_base;
+  void* debug_ns;                                   /* optional: 8 uint64, CTA 0's accumulated ns per stage (NULL = off) */
 } g4_align_loop_desc;
 size_t geo4d_align_loop_part_floats(int n_images_local, int chunks);
 int geo4d_align_loop_record_doubles(int max_images_per_rank, int G);

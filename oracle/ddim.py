@@ -140,8 +140,9 @@ def rescale_noise_cfg(noise_cfg, noise_pred_text, guidance_rescale=0.0):
 @torch.no_grad()
 def ddim_sample(apply_model: Callable, x_T: torch.Tensor, sch: Schedule, S: int,
                 spacing="uniform_trailing", eta=0.0, cfg_scale=1.0, apply_model_uncond=None,
-                guidance_rescale=0.0, noise_fn=None):
-    """ddim.py:134-203 loop with the v-parameterisation; apply_model(x, t_long[b]) -> v."""
+                guidance_rescale=0.0, noise_fn=None, apply_model_uncond_img=None, cfg_img=None):
+    """ddim.py:134-203 loop with the v-parameterisation; apply_model(x, t_long[b]) -> v.
+    With apply_model_uncond_img the 3-way guidance of ddim_multiplecond.py:226-236 is used."""
     tab = make_ddim_tables(sch, S, spacing, eta)
     x = x_T
     b = x.shape[0]
@@ -153,7 +154,11 @@ def ddim_sample(apply_model: Callable, x_T: torch.Tensor, sch: Schedule, S: int,
         if apply_model_uncond is not None and cfg_scale != 1.0:
             v_u = apply_model_uncond(x, ts)
             v_c = v
-            v = v_u + cfg_scale * (v_c - v_u)
+            if apply_model_uncond_img is not None:
+                v_ui = apply_model_uncond_img(x, ts)
+                v = v_u + (cfg_scale if cfg_img is None else cfg_img) * (v_ui - v_u) + cfg_scale * (v_c - v_ui)
+            else:
+                v = v_u + cfg_scale * (v_c - v_u)
             if guidance_rescale > 0.0:
                 v = rescale_noise_cfg(v, v_c, guidance_rescale)
         noise = noise_fn(x.shape) if (noise_fn is not None and eta > 0) else None

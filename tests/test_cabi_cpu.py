@@ -31,7 +31,7 @@ def test_exports_every_declared_symbol(lib):
 
 
 def test_abi_version_and_error_string(lib):
-    assert lib.geo4d_abi_version() == 2
+    assert lib.geo4d_abi_version() == 3
     lib.geo4d_last_error.restype = ctypes.c_char_p
     assert isinstance(lib.geo4d_last_error(), bytes)
 

@@ -316,3 +316,41 @@ def test_ddim_step_counter_gather(cuda_device):
     o = torch.empty(40, device="cuda")
     ops.gather_row(tab, idx, o)
     assert torch.equal(o, tab[1])
+
+
+@pytest.mark.parametrize("split", [2, 5, 16])
+def test_split_k_matches_fused_path(cuda_device, monkeypatch, split):
+    """Split-K tap-GEMM (the 5x8 level: 640 rows, K = 9 x 1280): partial fp32 planes + ordered reduce with the full
+    epilogue (bias, per-frame embedding row, residual) vs the single-pass kernel and vs fp32 torch."""
+    from geo4d_b200 import ops
+    monkeypatch.setattr(ops, "_AUTOTUNE", False)
+    g = torch.Generator(device="cuda").manual_seed(21)
+    N, H, W, Cin, Cout = 16, 5, 8, 1280, 1280
+    x = torch.randn(N, Cin, H, W, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / (9 * Cin) ** 0.5).bfloat16()
+    b = torch.randn(Cout, device="cuda", generator=g)
+    rb = torch.randn(1, Cout, device="cuda", generator=g)
+    res = torch.randn(N * H * W, Cout, device="cuda", generator=g).bfloat16()
+    ref = (F.conv2d(x.float(), w.float(), b, padding=1) + rb[:, :, None, None]).permute(0, 2, 3, 1).reshape(N * H * W, Cout) \
+        + res.float()
+    x2 = x.permute(0, 2, 3, 1).reshape(N * H * W, Cin).contiguous()
+    w9 = w.permute(2, 3, 0, 1).reshape(9, Cout, Cin).contiguous()
+    monkeypatch.setattr(ops, "_FORCE_TILE", (256, 1))
+    monkeypatch.setattr(ops, "_FORCE_SPLIT", 1)
+    base = ops.conv3x3(x2, N, H, W, w9, b, row_bias=rb, rows_per_bias=N * H * W, residual=res)
+    monkeypatch.setattr(ops, "_FORCE_SPLIT", split)
+    out = ops.conv3x3(x2, N, H, W, w9, b, row_bias=rb, rows_per_bias=N * H * W, residual=res)
+    out2 = ops.conv3x3(x2, N, H, W, w9, b, row_bias=rb, rows_per_bias=N * H * W, residual=res)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)                      # ordered reduction: bit-reproducible
+    assert _rel(out, ref) < BF16_TOL and _rel(base, ref) < BF16_TOL
+    assert _rel(out, base) < 3e-3                      # same products, different fp32 summation order, bf16 output
+    # fp32 output + SiLU through the reduce pass
+    wl = (torch.randn(256, 2560, device="cuda", generator=g) / 50).bfloat16()
+    xl = torch.randn(640, 2560, device="cuda", generator=g).bfloat16()
+    bl = torch.randn(256, device="cuda", generator=g)
+    o = ops.linear(xl, wl, bl, act=ops.ACT_SILU, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert _rel(o, F.silu(xl.float() @ wl.float().t() + bl)) < 1e-4
+    monkeypatch.setattr(ops, "_FORCE_TILE", None)
+    monkeypatch.setattr(ops, "_FORCE_SPLIT", None)
