@@ -352,7 +352,9 @@ def run_b200(args, rank, world, local):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a rank that dies or diverges must not leave the others blocked for NCCL's default 10 minutes
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
     H, W, T = args.height, args.width, args.frames
     model, pm_vae, cfg = synthetic.build_model(device=dev, seed=0)
     pipe = Geo4DPipeline(model, pm_vae, ddim_steps=args.ddim_steps, postprocess=dict(cfg["postprocess"], silent=True,

@@ -438,9 +438,7 @@ class LightPointCloudGroupOptimizer(nn.Module):
         # all-gathered; the sequential window chain below only composes them with each window's registration.
         local = None
         if not chain_pnp:
-            world, rank = 1, 0
-            if self.shard_sub_alignments and torch.distributed.is_available() and torch.distributed.is_initialized():
-                world, rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
+            world, rank = self._dist_sub()
             from . import sharding
             mine = sharding.windows_for_rank(G, rank, world) if world > 1 else list(range(G))
             per = -(-G // world)
@@ -604,9 +602,7 @@ class LightPointCloudGroupOptimizer(nn.Module):
             parts = [solve([g]) for g in sel]
             return torch.cat([p[0] for p in parts], 0), np.concatenate([p[1] for p in parts])
 
-        world, rank = 1, 0
-        if self.shard_sub_alignments and torch.distributed.is_available() and torch.distributed.is_initialized():
-            world, rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
+        world, rank = self._dist_sub()
         if world > 1 and G > 1:
             from . import sharding
             per = -(-G // world)
@@ -797,6 +793,16 @@ class LightPointCloudGroupOptimizer(nn.Module):
         for _ in range(it, it1):
             graph.replay()
         ops.note_replay(nk, it1 - it)
+
+    def _dist_sub(self):
+        """(world, rank) for the per-window sub-problems (PnP initialisation, LAD fits) split round-robin over the
+        ranks; (1, 0) on one GPU, for a single window, or when sharding is switched off (GEO4D_ALIGN_SHARD=0: a rank
+        that runs an alignment on its own must not enter collectives the other ranks do not)."""
+        if self.shard_sub_alignments and self.n_groups > 1 and torch.distributed.is_available() \
+                and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1 \
+                and os.environ.get("GEO4D_ALIGN_SHARD", "1") != "0":
+            return torch.distributed.get_world_size(), torch.distributed.get_rank()
+        return 1, 0
 
     # ------------------------------------------------------------------ persistent loop engine
     def _dist(self):

@@ -23,6 +23,9 @@ struct AttnArgs {
   int B, H, Lq, Lk;
   int n_qtiles, n_kvtiles;
   int kv_batch_div;  // K/V batch index = b / kv_batch_div (text keys shared by the frames of a clip)
+  // second, independently normalised key/value set (image cross-attention, attention.py:203-207): its tiles follow the
+  // first set's in the same CTA, O2 accumulates in its own TMEM columns and the epilogue stores O1/l1 + O2/l2
+  int Lk2, n_kvtiles2, kv_batch_div2;
   int accumulate;
   float scale_log2;  // scale * log2(e)
   void* out;
@@ -36,7 +39,8 @@ constexpr int AT_SMEM = AT_Q_BYTES + 4 * AT_KV_BYTES + AT_P_BYTES;  // 112 KB
 
 __global__ void __launch_bounds__(192, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const AttnArgs args) {
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmK2,
+                const __grid_constant__ CUtensorMap tmV2, const AttnArgs args) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bars[13];
   __shared__ uint32_t tmem_slot;
@@ -60,12 +64,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int h = bh % args.H;
   const int b = bh / args.H;
   const int bkv = b / args.kv_batch_div;
-  const int nkv = args.n_kvtiles;
+  const int nkv1 = args.n_kvtiles;
+  const int nkv = nkv1 + args.n_kvtiles2;   // tiles j >= nkv1 belong to the second key/value set
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
+    if (args.n_kvtiles2) { tma_prefetch_desc(&tmK2); tma_prefetch_desc(&tmV2); }
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&k_full[s], 1);
@@ -89,7 +95,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_base = tmem_slot;
   pdl_grid_sync();
   const uint32_t tS = tmem_base;        // 128 columns
-  const uint32_t tO = tmem_base + 128;  // 64 columns
+  const uint32_t tO = tmem_base + 128;  // 64 columns (first set), + 64 columns at 192 for the second set
 
   if (warp == 0) {
     if (lane == 0) {
@@ -98,12 +104,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int j = 0; j < nkv; ++j) {
         const int st = j & 1;
         const uint32_t ph = (j >> 1) & 1;
+        const bool second = j >= nkv1;
+        const int row0 = (second ? j - nkv1 : j) * 128;
+        const int bb = second ? b / args.kv_batch_div2 : bkv;
         mbar_wait(&k_empty[st], ph ^ 1);
         mbar_expect_tx(&k_full[st], AT_KV_BYTES);
-        tma_load_4d(sK + st * AT_KV_BYTES, &tmK, &k_full[st], 0, h, j * 128, bkv);
+        tma_load_4d(sK + st * AT_KV_BYTES, second ? &tmK2 : &tmK, &k_full[st], 0, h, row0, bb);
         mbar_wait(&v_empty[st], ph ^ 1);
         mbar_expect_tx(&v_full[st], AT_KV_BYTES);
-        tma_load_4d(sV + st * AT_KV_BYTES, &tmV, &v_full[st], 0, h, j * 128, bkv);
+        tma_load_4d(sV + st * AT_KV_BYTES, second ? &tmV2 : &tmV, &v_full[st], 0, h, row0, bb);
       }
     }
   } else if (warp == 1) {
@@ -138,12 +147,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&v_full[st], ph);
         mbar_wait(p_ready, j & 1);
         tc_fence_after();
+        const uint32_t tOj = j >= nkv1 ? tO + 64 : tO;          // each key/value set has its own accumulator
+        const int jj = j >= nkv1 ? j - nkv1 : j;
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_ss(tO, make_sw128_desc(aP + kb * 16384 + kk * 32, 16, 1024),
-                    make_sw128_desc(aV + kb * 8192 + kk * 2048, 1024, 1024), idesc_pv, (j | kb | kk) != 0);
+            umma_ss(tOj, make_sw128_desc(aP + kb * 16384 + kk * 32, 16, 1024),
+                    make_sw128_desc(aV + kb * 8192 + kk * 2048, 1024, 1024), idesc_pv, (jj | kb | kk) != 0);
         umma_commit(&v_empty[st]);
         umma_commit(pv_done);
       }
@@ -154,9 +165,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int r = qd * 32 + lane;  // query row within the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
     const float sl2 = args.scale_log2;
-    float m = -INFINITY, l = 0.f;
+    float m = -INFINITY, l = 0.f, l_first = 1.f;
     for (int j = 0; j < nkv; ++j) {
-      const int kv_valid = min(128, args.Lk - j * 128);  // keys of this tile that exist
+      if (j == nkv1 && j > 0) { l_first = l; m = -INFINITY; l = 0.f; }   // second set: a softmax of its own
+      const bool second = j >= nkv1;
+      const int jj = second ? j - nkv1 : j;
+      const uint32_t tOj = second ? tO + 64 : tO;
+      const int kv_valid = min(128, (second ? args.Lk2 : args.Lk) - jj * 128);  // keys of this tile that exist
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       // the whole score row goes to registers with ONE TMEM round trip; S is then free for QK_{j+1}
@@ -185,15 +200,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // the previous PV must have retired before O is rescaled / P is overwritten
       mbar_wait(pv_done, (j & 1) ^ 1);
       tc_fence_after();
-      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+      if (jj > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
           uint32_t v[32];
-          tmem_ld32(tO + lane_off + c * 32, v);
+          tmem_ld32(tOj + lane_off + c * 32, v);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-          tmem_st32(tO + lane_off + c * 32, v);
+          tmem_st32(tOj + lane_off + c * 32, v);
         }
         tmem_st_wait();
       }
@@ -231,12 +246,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_wait(pv_done, (nkv - 1) & 1);
     tc_fence_after();
     const int lq = qt * 128 + r;
-    const float inv_l = 1.0f / l;
+    const bool two = args.n_kvtiles2 > 0;
+    const float inv_l = two ? 1.0f / l_first : 1.0f / l;
+    const float inv_l2 = 1.0f / l;
     __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(args.out) + ((long long)b * args.Lq + lq) * args.ldo + h * 64;
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
+      uint32_t v[32], v2[32];
       tmem_ld32(tO + lane_off + c * 32, v);
+      if (two) tmem_ld32(tO + 64 + lane_off + c * 32, v2);
       tmem_ld_wait();
       if (lq < args.Lq) {
         uint4* o4 = reinterpret_cast<uint4*>(orow + c * 32);
@@ -244,7 +262,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int qq = 0; qq < 4; ++qq) {
           float o[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[8 * qq + i]) * inv_l;
+          for (int i = 0; i < 8; ++i) {
+            o[i] = __uint_as_float(v[8 * qq + i]) * inv_l;
+            if (two) o[i] = fmaf(__uint_as_float(v2[8 * qq + i]), inv_l2, o[i]);
+          }
           if (args.accumulate) {
             const uint4 pr = o4[qq];
             float2 f;
@@ -275,17 +296,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 using namespace g4;
 
-extern "C" int geo4d_attention(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* out,
-                               int64_t ldo, int B, int H, int Lq, int Lk, int kv_batch_div, int accumulate, float scale,
-                               g4_stream_t stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+static int attention_impl(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, int Lk, int kv_batch_div,
+                          const void* k2, const void* v2, int64_t ldkv2, int Lk2, int kv_batch_div2, void* out, int64_t ldo,
+                          int B, int H, int Lq, int accumulate, float scale, cudaStream_t stream) {
   if (!q || !k || !v || !out) { set_last_error("attention: null pointer"); return G4_ERR_BAD_ARG; }
   if (B < 1 || H < 1 || Lq < 1 || Lk < 1 || kv_batch_div < 1) { set_last_error("attention: bad sizes B=%d H=%d Lq=%d Lk=%d", B, H, Lq, Lk); return G4_ERR_BAD_ARG; }
   if (ldq % 8 || ldkv % 8 || ldo % 8 || ((uintptr_t)q & 15) || ((uintptr_t)k & 15) || ((uintptr_t)v & 15) ||
       ((uintptr_t)out & 15)) {
     set_last_error("attention: pointers must be 16-byte aligned and leading dims multiples of 8"); return G4_ERR_BAD_ARG;
   }
-  CUtensorMap tmQ, tmK, tmV;
+  const bool two = k2 != nullptr;
+  if (two && (!v2 || Lk2 < 1 || kv_batch_div2 < 1 || ldkv2 % 8 || ((uintptr_t)k2 & 15) || ((uintptr_t)v2 & 15))) {
+    set_last_error("attention: bad second key/value set"); return G4_ERR_BAD_ARG;
+  }
+  CUtensorMap tmQ, tmK, tmV, tmK2, tmV2;
   {
     uint64_t dims[4] = {64, (uint64_t)H, (uint64_t)Lq, (uint64_t)B};
     uint64_t str[3] = {128, (uint64_t)ldq * 2, (uint64_t)ldq * 2 * (uint64_t)Lq};
@@ -301,22 +325,45 @@ extern "C" int geo4d_attention(const void* q, int64_t ldq, const void* k, const 
     if (rc) return rc;
     rc = make_tmap_bf16(&tmV, v, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
+    tmK2 = tmK; tmV2 = tmV;
+  }
+  if (two) {
+    uint64_t dims[4] = {64, (uint64_t)H, (uint64_t)Lk2, (uint64_t)((B + kv_batch_div2 - 1) / kv_batch_div2)};
+    uint64_t str[3] = {128, (uint64_t)ldkv2 * 2, (uint64_t)ldkv2 * 2 * (uint64_t)Lk2};
+    uint32_t box[4] = {64, 1, 128, 1};
+    int rc = make_tmap_bf16(&tmK2, k2, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tmV2, v2, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
   }
   AttnArgs a;
   a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk;
   a.n_qtiles = (Lq + 127) / 128;
   a.n_kvtiles = (Lk + 127) / 128;
   a.kv_batch_div = kv_batch_div; a.accumulate = accumulate;
+  a.Lk2 = two ? Lk2 : 0; a.n_kvtiles2 = two ? (Lk2 + 127) / 128 : 0; a.kv_batch_div2 = two ? kv_batch_div2 : 1;
   a.scale_log2 = scale * 1.4426950408889634f;
   a.out = out; a.ldo = ldo;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
-    if (e != cudaSuccess) { set_last_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return G4_ERR_CUDA; }
-    attr_set = true;
-  }
+  cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);   // per device, cheap
+  if (e != cudaSuccess) { set_last_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return G4_ERR_CUDA; }
   const long long grid = (long long)a.n_qtiles * B * H;
   if (grid > 2147483647ll) { set_last_error("attention: grid too large"); return G4_ERR_UNSUPPORTED; }
-  launch_pdl(attn_fwd_kernel, dim3((int)grid), dim3(192), AT_SMEM, stream, tmQ, tmK, tmV, a);
+  launch_pdl(attn_fwd_kernel, dim3((int)grid), dim3(192), AT_SMEM, stream, tmQ, tmK, tmV, tmK2, tmV2, a);
   return check_launch("attention");
+}
+
+extern "C" int geo4d_attention(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* out,
+                               int64_t ldo, int B, int H, int Lq, int Lk, int kv_batch_div, int accumulate, float scale,
+                               g4_stream_t stream_) {
+  return attention_impl(q, ldq, k, v, ldkv, Lk, kv_batch_div, nullptr, nullptr, 0, 0, 1, out, ldo, B, H, Lq, accumulate, scale,
+                        reinterpret_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int geo4d_cross_attention2(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, int Lk,
+                                      int kv_batch_div, const void* k2, const void* v2, int64_t ldkv2, int Lk2,
+                                      int kv_batch_div2, void* out, int64_t ldo, int B, int H, int Lq, float scale,
+                                      g4_stream_t stream_) {
+  if (!k2 || !v2) { set_last_error("cross_attention2: second key/value set is null"); return G4_ERR_BAD_ARG; }
+  return attention_impl(q, ldq, k, v, ldkv, Lk, kv_batch_div, k2, v2, ldkv2, Lk2, kv_batch_div2, out, ldo, B, H, Lq, 0, scale,
+                        reinterpret_cast<cudaStream_t>(stream_));
 }

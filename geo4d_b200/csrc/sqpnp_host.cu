@@ -257,3 +257,26 @@ extern "C" int geo4d_sqpnp_from_moments(const double* mom, double f, double* R_o
   memcpy(t_out, best_t, sizeof(best_t));
   return 1;
 }
+
+// Batch form: n independent (moments, focal) problems, solved on up to `threads` host threads (every problem is a
+// few hundred microseconds of dense 9x9 / 15x15 algebra; the per-frame hypothesis sets of the PnP initialisation
+// are solved together).  ok_out[i] = 1 on success.  HOST function, no CUDA.
+#include <thread>
+#include <vector>
+extern "C" int geo4d_sqpnp_from_moments_batch(const double* mom, const double* f, int n, double* R_out, double* t_out,
+                                              int* ok_out, int threads) {
+  if (!mom || !f || !R_out || !t_out || !ok_out || n < 0) return 0;
+  if (threads < 1) threads = 1;
+  if (threads > n) threads = n;
+  auto work = [&](int w) {
+    for (int i = w; i < n; i += threads)
+      ok_out[i] = geo4d_sqpnp_from_moments(mom + (size_t)i * 41, f[i], R_out + (size_t)i * 9, t_out + (size_t)i * 3);
+  };
+  if (threads <= 1) { work(0); return 1; }
+  std::vector<std::thread> pool;
+  pool.reserve(threads - 1);
+  for (int w = 1; w < threads; ++w) pool.emplace_back(work, w);
+  work(0);
+  for (auto& th : pool) th.join();
+  return 1;
+}

@@ -269,14 +269,32 @@ def sqpnp_from_moments_native(mom: np.ndarray, f: float):
     return (out[:9].reshape(3, 3).copy(), out[9:].copy()) if ok else None
 
 
+_SQPNP_BATCH_FN = None
+
+
 def sqpnp_from_moments_batch(moms: np.ndarray, focals) -> list:
-    """sqpnp_from_moments for B (moments, focal) pairs.  Default: the native host solver, one call per pair;
-    GEO4D_SQPNP=numpy keeps everything in NumPy with the linear algebra batched (cases that need more than the
-    smallest eigenvector, or that hit a singular system, fall back to the scalar routine)."""
+    """sqpnp_from_moments for B (moments, focal) pairs.  Default: the native host solver on a few host threads
+    (geo4d_sqpnp_from_moments_batch); GEO4D_SQPNP=numpy keeps everything in NumPy with the linear algebra batched
+    (cases that need more than the smallest eigenvector, or that hit a singular system, fall back to the scalar
+    routine)."""
+    global _SQPNP_BATCH_FN
     B = len(focals)
+    if B == 0:
+        return []
     if os.environ.get("GEO4D_SQPNP", "native") != "numpy":
-        moms2 = np.asarray(moms, dtype=np.float64).reshape(B, -1)
-        return [sqpnp_from_moments_native(moms2[i], float(focals[i])) for i in range(B)]
+        import ctypes as C
+        if _SQPNP_BATCH_FN is None:
+            from ._cabi import lib
+            fn = lib().geo4d_sqpnp_from_moments_batch
+            fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+            fn.restype = C.c_int
+            _SQPNP_BATCH_FN = fn
+        m = np.ascontiguousarray(np.asarray(moms, dtype=np.float64).reshape(B, -1)[:, :41])
+        f = np.ascontiguousarray(np.asarray(focals, dtype=np.float64).reshape(B))
+        R, t, ok = np.empty((B, 9)), np.empty((B, 3)), np.zeros(B, dtype=np.int32)
+        _SQPNP_BATCH_FN(m.ctypes.data, f.ctypes.data, B, R.ctypes.data, t.ctypes.data, ok.ctypes.data,
+                        min(B, 8, os.cpu_count() or 1))
+        return [(R[i].reshape(3, 3).copy(), t[i].copy()) if ok[i] else None for i in range(B)]
     out = [None] * B
     moms = np.asarray(moms, dtype=np.float64).reshape(B, -1)
     f = np.asarray(focals, dtype=np.float64)
@@ -387,8 +405,34 @@ def gpu_fast_pnp_frames(ops, pts: "torch.Tensor", conf: "torch.Tensor", H: int, 
             im_poses[img] = np.eye(4)
 
 
+def _minimal_sample_moments(pts, conf, cand, W, cx, cy):
+    """41 SQPnP moments of 4-point samples.  pts [..., D, 3], conf [..., D] hold D >= 4 candidate pixels per sample
+    (pixel indices `cand`); the first 4 with conf > 0.5 form the sample.  Returns (mom [..., 41], usable [...])."""
+    valid = conf > 0.5
+    order = np.argsort(~valid, axis=-1, kind="stable")[..., :4]          # first four valid draws
+    usable = np.take_along_axis(valid, order, -1).all(-1)
+    m = np.take_along_axis(pts, order[..., None], -2).astype(np.float64)  # [..., 4, 3]
+    pix = np.take_along_axis(cand, order, -1)
+    du, dv = (pix % W) - cx, (pix // W) - cy
+    r2 = du * du + dv * dv
+    mom = np.zeros(m.shape[:-2] + (41,))
+    mom[..., 0], mom[..., 1], mom[..., 2], mom[..., 3] = 4.0, du.sum(-1), dv.sum(-1), r2.sum(-1)
+    mom[..., 4:7] = m.sum(-2)
+    mom[..., 7:10] = (du[..., None] * m).sum(-2)
+    mom[..., 10:13] = (dv[..., None] * m).sum(-2)
+    mom[..., 13:16] = (r2[..., None] * m).sum(-2)
+    mm = np.stack([m[..., 0] * m[..., 0], m[..., 0] * m[..., 1], m[..., 0] * m[..., 2], m[..., 1] * m[..., 1],
+                   m[..., 1] * m[..., 2], m[..., 2] * m[..., 2]], -1)          # [..., 4, 6]
+    mom[..., 16:22] = mm.sum(-2)
+    mom[..., 22:28] = (du[..., None] * mm).sum(-2)
+    mom[..., 28:34] = (dv[..., None] * mm).sum(-2)
+    mom[..., 34:40] = (r2[..., None] * mm).sum(-2)
+    mom[..., 40] = 4.0
+    return mom, usable
+
+
 def gpu_fast_pnp_windows(ops, pred: "torch.Tensor", conf: "torch.Tensor", H: int, W: int, focal_group,
-                         niter_PnP: int = 10, thr_px: float = 5.0):
+                         niter_PnP: int = 10, thr_px: float = 5.0, seed: int = 0):
     """fast_pnp (init_im_poses.py:824-865) for every frame of several windows, each in its window's OWN frame.
 
     pred [Gm, gs, HW, 3], conf [Gm, gs, HW]: the windows this rank initialises.  PnP is equivariant under the
@@ -396,8 +440,15 @@ def gpu_fast_pnp_windows(ops, pred: "torch.Tensor", conf: "torch.Tensor", H: int
     [R_c2w' | t'] = [R R_c2w | s R t_c2w + T], identical consensus sets), so it does not have to wait for the
     sequential window chain of align_group_prefix: windows are independent here, which is what lets the ranks
     split them, and frame k of all Gm windows shares ONE moments launch and ONE device -> host read.
-    Inside a window the reference's focal chain is kept: frame 0 starts from the window's focal (the LM fit),
-    frame k from frame k-1's result (after a failed PnP: the last successful one in this window).
+
+    RANSAC as the reference runs it (cv2.solvePnPRansac, iterationsCount = niter_PnP, 5 px, SQPNP): per frame the
+    hypotheses are the SQPnP solutions of `niter_PnP` seeded minimal 4-point samples plus the least-squares solution
+    over all masked points (one per tentative focal); every hypothesis is scored by its consensus set in a single
+    launch (geo4d_pnp_moments with one candidate per hypothesis), the best one is re-fitted on its consensus set --
+    what OpenCV does after its RANSAC loop.  Ties go to the all-points solution, so clean point maps give the same
+    result as a plain fit -> gate -> refit.  Inside a window the reference's focal chain is kept: frame 0 starts
+    from the window's focal (the LM fit), frame k from frame k-1's result (after a failed PnP: the last successful
+    one in this window).
 
     Returns (focals [Gm, gs] (nan = PnP failed), c2w [Gm, gs, 4, 4] (window frame), ok [Gm, gs] bool)."""
     import torch
@@ -406,17 +457,28 @@ def gpu_fast_pnp_windows(ops, pred: "torch.Tensor", conf: "torch.Tensor", H: int
     cx, cy = W / 2, H / 2
     S = max(W, H)
     dev = pred.device
+    n_hyp = max(0, int(niter_PnP)) if os.environ.get("GEO4D_PNP_RANSAC", "1") != "0" else 0
     # frame-major copies: frame k of every window contiguous
     pts_t = pred.transpose(0, 1).contiguous()      # [gs, Gm, HW, 3]
     conf_t = conf.transpose(0, 1).contiguous()     # [gs, Gm, HW]
     mom_all = ops.pnp_moments(pts_t.view(gs * Gm, HW, 3), conf_t.view(gs * Gm, HW), gs * Gm, HW, W, cx, cy) \
         .cpu().numpy()[:, 0].reshape(gs, Gm, -1)   # focal-independent moments of every frame, one read
+    mom_min = usable = None
+    if n_hyp:
+        D = 16
+        cand = np.random.default_rng(seed).integers(0, HW, size=(gs, Gm, n_hyp * D))
+        idx = torch.from_numpy(cand).to(dev)
+        sp = torch.gather(pts_t, 2, idx.unsqueeze(-1).expand(-1, -1, -1, 3)).cpu().numpy()
+        sc = torch.gather(conf_t, 2, idx).cpu().numpy()
+        mom_min, usable = _minimal_sample_moments(sp.reshape(gs, Gm, n_hyp, D, 3), sc.reshape(gs, Gm, n_hyp, D),
+                                                  cand.reshape(gs, Gm, n_hyp, D), W, cx, cy)
     focals = np.full((Gm, gs), np.nan)
     c2w = np.tile(np.eye(4), (Gm, gs, 1, 1))
     ok = np.zeros((Gm, gs), dtype=bool)
     prev = [float(f) if f is not None and np.isfinite(f) and f > 0 else None for f in focal_group]
     for k in range(gs):
-        tent = []
+        # ---- hypotheses of frame k of every window: (moments, focal) problems, solved in one batch
+        probs_m, probs_f, owner = [], [], []
         for g in range(Gm):
             focal = prev[g]
             if focal is None:
@@ -424,39 +486,47 @@ def gpu_fast_pnp_windows(ops, pred: "torch.Tensor", conf: "torch.Tensor", H: int
             else:
                 lo, hi = -0.03 * S + focal, 0.03 * S + focal
                 t = [focal] + ([float(x) for x in np.geomspace(lo, hi, 2)] if lo > 0 else [])
-            tent.append([float(f) for f in t if np.isfinite(f) and f > 0])
-        sols = [sqpnp_from_moments_batch(np.repeat(mom_all[k, g][None], len(tent[g]), 0), tent[g]) for g in range(Gm)]
-        good = [[i for i, sol in enumerate(sols[g]) if sol is not None] for g in range(Gm)]
-        C = max((len(x) for x in good), default=0)
+            t = [float(f) for f in t if np.isfinite(f) and f > 0]
+            for f in t:                                   # least-squares hypothesis per tentative focal
+                probs_m.append(mom_all[k, g]); probs_f.append(f); owner.append(g)
+            if n_hyp and t:
+                for h in range(n_hyp):                     # minimal-sample hypotheses at the leading focal
+                    if usable[k, g, h]:
+                        probs_m.append(mom_min[k, g, h]); probs_f.append(t[0]); owner.append(g)
+        if not probs_f:
+            continue
+        sols = sqpnp_from_moments_batch(np.stack(probs_m), probs_f)
+        hyp = [[] for _ in range(Gm)]                      # per window: (R, t, focal)
+        for sol, f, g in zip(sols, probs_f, owner):
+            if sol is not None:
+                hyp[g].append((sol[0], sol[1], f))
+        C = max(len(x) for x in hyp)
         if C == 0:
             continue
         gate = np.zeros((Gm, C, 13), dtype=np.float32)
         gate[:, :, 11] = -1.0                      # padding candidates: R = 0, t_z = -1 puts every point behind the camera
         gate[:, :, 12] = 1.0
         for g in range(Gm):
-            for j, i in enumerate(good[g]):
-                R, t = sols[g][i]
+            for j, (R, t, f) in enumerate(hyp[g]):
                 gate[g, j, :12] = np.concatenate([R, t[:, None]], 1).reshape(12)
-                gate[g, j, 12] = tent[g][i]
+                gate[g, j, 12] = f
         mom_in = ops.pnp_moments(pts_t[k], conf_t[k], Gm, HW, W, cx, cy, gate=torch.from_numpy(gate).to(dev), ncand=C,
                                  thr_px=thr_px).cpu().numpy()
-        for g in range(Gm):
-            if not good[g]:
-                continue
-            refit = sqpnp_from_moments_batch(mom_in[g, :len(good[g])], [tent[g][i] for i in good[g]])
-            best = (0, None, None)
-            for j, i in enumerate(good[g]):
-                ninl = int(round(mom_in[g, j, 40]))
-                if ninl < 4 or ninl <= best[0]:
+        # ---- best consensus set per window (ties: earliest hypothesis = the all-points fit), re-fitted on it
+        order = [sorted(range(len(hyp[g])), key=lambda j: (-int(round(mom_in[g, j, 40])), j)) for g in range(Gm)]
+        for attempt in range(3):
+            todo = [(g, order[g][attempt]) for g in range(Gm)
+                    if not ok[g, k] and attempt < len(order[g]) and int(round(mom_in[g, order[g][attempt], 40])) >= 4]
+            if not todo:
+                break
+            refit = sqpnp_from_moments_batch(np.stack([mom_in[g, j] for g, j in todo]), [hyp[g][j][2] for g, j in todo])
+            for (g, j), sol in zip(todo, refit):
+                if sol is None:
                     continue
-                if refit[j] is not None:
-                    best = (ninl, refit[j], tent[g][i])
-            if best[0]:
-                R, t = best[1]
                 w2c = np.eye(4)
-                w2c[:3, :3], w2c[:3, 3] = R, t
-                focals[g, k], c2w[g, k], ok[g, k] = best[2], np.linalg.inv(w2c), True
-                prev[g] = float(best[2])
+                w2c[:3, :3], w2c[:3, 3] = sol
+                focals[g, k], c2w[g, k], ok[g, k] = hyp[g][j][2], np.linalg.inv(w2c), True
+                prev[g] = float(hyp[g][j][2])
     return focals, c2w, ok
 
 

@@ -329,6 +329,18 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     return out
 
 
+def cross_attention2(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, Lk: int, div: int, k2: torch.Tensor,
+                     v2: torch.Tensor, Lk2: int, div2: int, out: torch.Tensor, B: int, H: int, Lq: int,
+                     scale: float = 0.125) -> torch.Tensor:
+    """text + image cross-attention in one launch: out = softmax(q k^T) v + softmax(q k2^T) v2 (two softmaxes)."""
+    assert k.stride(0) == v.stride(0) and k2.stride(0) == v2.stride(0)
+    check(lib().geo4d_cross_attention2(_vp(q), C.c_int64(q.stride(0)), _vp(k), _vp(v), C.c_int64(k.stride(0)), Lk, div,
+                                       _vp(k2), _vp(v2), C.c_int64(k2.stride(0)), Lk2, div2, _vp(out),
+                                       C.c_int64(out.stride(0)), B, H, Lq, C.c_float(scale), _s()),
+          "geo4d_cross_attention2")
+    return out
+
+
 def temporal_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, B: int, T: int,
                        HW: int, heads: int, scale: float = 0.125) -> torch.Tensor:
     assert q.stride(0) == k.stride(0) == v.stride(0)

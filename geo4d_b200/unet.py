@@ -483,11 +483,13 @@ class UNetModel(nn.Module):
             kv_t, kv_i = spatial_kv
             cc = self._ctx_cache
             q2 = ops.linear(n2, P[f"{p}.attn2.q"])
-            ops.attention(q2, kv_t[:, :inner], kv_t[:, inner:], o, b * t, heads, hh * ww, cc["text_len"],
-                          kv_batch_div=t)
-            if kv_i is not None:
-                ops.attention(q2, kv_i[:, :inner], kv_i[:, inner:], o, b * t, heads, hh * ww, cc["img_len"],
-                              kv_batch_div=1 if cc["img_per_frame"] else t, accumulate=True)
+            if kv_i is not None:   # text + image branch in one launch (two softmaxes sharing the Q tile)
+                ops.cross_attention2(q2, kv_t[:, :inner], kv_t[:, inner:], cc["text_len"], t, kv_i[:, :inner],
+                                     kv_i[:, inner:], cc["img_len"], 1 if cc["img_per_frame"] else t, o, b * t, heads,
+                                     hh * ww)
+            else:
+                ops.attention(q2, kv_t[:, :inner], kv_t[:, inner:], o, b * t, heads, hh * ww, cc["text_len"],
+                              kv_batch_div=t)
         else:
             qkv2 = ops.linear(n2, P[f"{p}.attn2.qkv"])
             ops.temporal_attention(qkv2[:, :inner], qkv2[:, inner:2 * inner], qkv2[:, 2 * inner:], o, b, t,

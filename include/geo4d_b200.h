@@ -126,6 +126,14 @@ int geo4d_attention(const void* q, int64_t ldq, const void* k, const void* v, in
                     int64_t ldo, int B, int H, int Lq, int Lk, int kv_batch_div, int accumulate, float scale,
                     g4_stream_t stream);
 
+/* Both cross-attention branches of CrossAttention.efficient_forward in ONE launch (attention.py:166-207): text keys
+ * (k, v: Lk = 77, shared by the frames of a clip through kv_batch_div) and image keys (k2, v2: Lk2 = 16 per frame)
+ * are attended with the same Q tile and two independent softmaxes; out = softmax(QK^T)V + softmax(QK2^T)V2. */
+int geo4d_cross_attention2(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, int Lk,
+                           int kv_batch_div, const void* k2, const void* v2, int64_t ldkv2, int Lk2,
+                           int kv_batch_div2, void* out, int64_t ldo, int B, int H, int Lq, float scale,
+                           g4_stream_t stream);
+
 /* Temporal self-attention over <=16 frame tokens per (pixel, head) (CrossAttention.forward
  * attention.py:81-144 as used by TemporalTransformer :365-412).  Row of (b, t, p) = (b*T + t)*HW + p. */
 int geo4d_temporal_attention(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo,
@@ -209,6 +217,9 @@ int geo4d_lad_step(const float* x, const float* y, int64_t n_per_group, int G, f
  * cv2.solvePnPRansac(flags=SOLVEPNP_SQPNP) in fast_pnp, init_im_poses.py:824-865).  Writes the world-to-camera
  * rotation (row-major 3x3) and translation; returns 1 on success, 0 if there is no valid solution. */
 int geo4d_sqpnp_from_moments(const double* mom, double f, double* R_out, double* t_out);
+/* n problems at once on up to `threads` host threads; mom [n][41], R_out [n][9], t_out [n][3], ok_out [n]. */
+int geo4d_sqpnp_from_moments_batch(const double* mom, const double* f, int n, double* R_out, double* t_out,
+                                   int* ok_out, int threads);
 /* The whole fit (up to `iters` iterations of geo4d_lad_step, same arithmetic and early exit) in one cooperative
  * launch with a per-window grid barrier; needs G <= number of SMs.  acc as above (4*G doubles, zero on entry). */
 int geo4d_lad_fit(const float* x, const float* y, int64_t n_per_group, int G, float* state, double* acc, float lr,

@@ -79,8 +79,8 @@ def main():
         model.load_state_dict(sd["state_dict"] if "state_dict" in sd else sd, strict=True)
         pm_vae = instantiate_from_config(cfg["pointmap_vae_config"]).to(dev)
         vsd = torch.load(cfg["vae_path"], map_location="cpu")["state_dict"]
-        pm_vae.load_state_dict({k[len("model."):] if k.startswith("model.") else k: v for k, v in vsd.items()},
-                               strict=True)
+        # infer_geo4d.py:343-347: only the keys under 'model.' belong to the fine-tuned VAE, the rest is dropped
+        pm_vae.load_state_dict({k[6:]: v for k, v in vsd.items() if k.startswith("model.")}, strict=True)
         model.prepare(); pm_vae.prepare()
         if args.cond_path is None:
             raise SystemExit("--cond_path is required with a real checkpoint (conditioning towers are out of scope)")

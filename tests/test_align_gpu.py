@@ -342,3 +342,41 @@ def test_loop_engine_shapes(cuda_device, monkeypatch, T, H, W):
         d = float((getattr(a, name).detach() - getattr(f, name).detach()).abs().max())
         assert d < 2e-4, (name, d)
     assert abs(la - lf) / la < 1e-3
+
+
+@pytest.mark.parametrize("frac", [0.0, 0.3])
+def test_window_pnp_vs_cv2_ransac_with_structured_outliers(cuda_device, frac):
+    """with 30 % of the image moved rigidly (a biasing outlier block) a plain fit -> gate ->
+    refit converges to the wrong consensus set; the windowed PnP scores RANSAC-style minimal-sample hypotheses like
+    cv2.solvePnPRansac(iterationsCount=10, 5 px, SQPNP) (init_im_poses.py:824-865) and must land on the same pose."""
+    from geo4d_b200 import init_solvers as isv, ops
+    H, W, f = 96, 128, 0.9 * 128
+    gs = 3
+    frames, gts = [], []
+    for k in range(gs):
+        a = 0.2 + 0.05 * k
+        c2w = np.eye(4)
+        c2w[:3, :3] = [[math.cos(a), 0, math.sin(a)], [0, 1, 0], [-math.sin(a), 0, math.cos(a)]]
+        c2w[:3, 3] = [0.2 + 0.1 * k, -0.1, 0.05 * k]
+        pts = _pinhole_scene(H, W, f, c2w, seed=k)
+        wc = int(W * frac)
+        if wc:
+            b = 0.5
+            Rb = np.array([[math.cos(b), -math.sin(b), 0], [math.sin(b), math.cos(b), 0], [0, 0, 1]], dtype=np.float32)
+            blk = pts[:, :wc].reshape(-1, 3)
+            pts[:, :wc] = ((blk - blk.mean(0)) @ Rb.T + blk.mean(0) + np.float32([0.6, 0.3, -0.4])).reshape(H, wc, 3)
+        frames.append(pts)
+        gts.append(c2w)
+    pred = torch.tensor(np.stack(frames)).reshape(1, gs, H * W, 3).to(cuda_device)
+    conf = torch.ones(1, gs, H * W, device=cuda_device)
+    focals, c2w, ok = isv.gpu_fast_pnp_windows(ops, pred, conf, H, W, [f * 1.01], niter_PnP=10)
+    msk = np.ones((H, W), dtype=bool)
+    prev = f * 1.01
+    for k in range(gs):
+        assert ok[0, k]
+        ref = isv.fast_pnp(frames[k], prev, msk, 10)
+        assert ref is not None
+        assert np.abs(c2w[0, k] - gts[k]).max() < 1e-2, (k, np.abs(c2w[0, k] - gts[k]).max())
+        assert np.abs(c2w[0, k] - ref[1]).max() < 5e-3, (k, np.abs(c2w[0, k] - ref[1]).max())
+        assert abs(focals[0, k] - ref[0]) < 1e-6 * f + 1e-9 or abs(focals[0, k] - ref[0]) / f < 0.04
+        prev = focals[0, k]

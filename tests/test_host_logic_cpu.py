@@ -67,6 +67,29 @@ def test_config_aliases_resolve_reference_targets():
     assert cfg["postprocess"]["n_iter"] == 500
 
 
+def test_config_equals_the_references_parsed_yaml_key_by_key(golden_dir):
+    """configs/inference_geo4d.yaml vs tests/golden/config_ref.json (= yaml.safe_load of the reference's
+    configs/inference_geo4d.yaml, written by the build container): every section, every key, every value."""
+    import json
+    from geo4d_b200.config import load_yaml
+    mine = load_yaml(os.path.join(os.path.dirname(os.path.dirname(__file__)), "configs", "inference_geo4d.yaml"))
+    ref = json.load(open(os.path.join(golden_dir, "config_ref.json")))
+
+    def walk(a, b, path):
+        assert type(a) is type(b) or (isinstance(a, (int, float)) and isinstance(b, (int, float))), path
+        if isinstance(a, dict):
+            assert sorted(a.keys()) == sorted(b.keys()), (path, sorted(a.keys()), sorted(b.keys()))
+            for k in a:
+                walk(a[k], b[k], path + "." + str(k))
+        elif isinstance(a, list):
+            assert len(a) == len(b), path
+            for i, (x, y) in enumerate(zip(a, b)):
+                walk(x, y, f"{path}[{i}]")
+        else:
+            assert a == b, (path, a, b)
+    walk(mine, ref, "cfg")
+
+
 def test_geglu_interleave_and_tile_picker():
     from geo4d_b200.unet import _interleave32
     from geo4d_b200.ops import pick_box

@@ -244,6 +244,32 @@ def test_attention(cuda_device, B, H, Lq, Lk, kv_shared, accumulate):
     assert _rel(out, ref) < 4e-3
 
 
+@pytest.mark.parametrize("B,T,H,Lq,Lk1,Lk2", [(8, 4, 5, 300, 77, 16), (4, 4, 3, 128, 200, 16), (16, 16, 5, 2560, 77, 16),
+                                             (2, 2, 10, 640, 77, 130)])
+def test_cross_attention_two_key_sets_one_launch(cuda_device, B, T, H, Lq, Lk1, Lk2):
+    """geo4d_cross_attention2: text keys shared by the T frames of a clip + per-frame image keys, two independent
+    softmaxes, summed (attention.py:166-207) -- vs the two-launch form and vs fp32 torch."""
+    from geo4d_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(Lq + Lk1)
+    inner = H * 64
+    q = torch.randn(B * Lq, inner, device="cuda", generator=g).bfloat16()
+    kv1 = torch.randn((B // T) * Lk1, 2 * inner, device="cuda", generator=g).bfloat16()
+    kv2 = torch.randn(B * Lk2, 2 * inner, device="cuda", generator=g).bfloat16()
+    out = torch.empty(B * Lq, inner, device="cuda", dtype=torch.bfloat16)
+    ops.cross_attention2(q, kv1[:, :inner], kv1[:, inner:], Lk1, T, kv2[:, :inner], kv2[:, inner:], Lk2, 1, out, B, H, Lq)
+    two = torch.empty_like(out)
+    ops.attention(q, kv1[:, :inner], kv1[:, inner:], two, B, H, Lq, Lk1, kv_batch_div=T)
+    ops.attention(q, kv2[:, :inner], kv2[:, inner:], two, B, H, Lq, Lk2, kv_batch_div=1, accumulate=True)
+    torch.cuda.synchronize()
+    k1 = kv1[:, :inner].reshape(B // T, Lk1, inner).repeat_interleave(T, dim=0)
+    v1 = kv1[:, inner:].reshape(B // T, Lk1, inner).repeat_interleave(T, dim=0)
+    k2, v2 = kv2[:, :inner].reshape(B, Lk2, inner), kv2[:, inner:].reshape(B, Lk2, inner)
+    qq = q.reshape(B, Lq, inner)
+    ref = (_attn_ref(qq, k1, v1, H, 0.125) + _attn_ref(qq, k2, v2, H, 0.125)).reshape(B * Lq, inner)
+    assert _rel(out, ref) < 4e-3
+    assert _rel(out, two) < 6e-3        # the two-launch form rounds the first branch to bf16 before adding the second
+
+
 @pytest.mark.parametrize("B,T,HW,H", [(1, 16, 160, 5), (2, 4, 128, 2), (1, 16, 40, 20), (1, 7, 33, 3)])
 def test_temporal_attention(cuda_device, B, T, HW, H):
     from geo4d_b200 import ops

@@ -70,3 +70,25 @@ def test_gather_group_records_world2():
             ret = m.dict()
             mp.spawn(_worker_groups, args=(2, port, n_groups, ret), nprocs=2, join=True)
             assert dict(ret) == {0: True, 1: True}
+
+
+def test_partition_images_is_contiguous_balanced_and_complete():
+    """image ranges of the sharded alignment loop: contiguous, cover every image once, balanced by (1 + windows
+    observing the image) -- including more ranks than images and a single rank"""
+    from geo4d_b200 import sharding
+    for edges, world in (([1] * 8 + [2] * 56 + [1] * 8, 8), ([1] * 16, 1), ([1] * 16, 2), ([2, 2, 2], 8),
+                         ([1] * 8 + [2] * 8 + [3] * 14 + [2] * 4 + [1] * 16, 4), ([1] * 72, 16)):
+        lo = sharding.partition_images(edges, world)
+        assert len(lo) == world + 1 and lo[0] == 0 and lo[-1] == len(edges)
+        assert all(b >= a for a, b in zip(lo, lo[1:]))
+        cost = [sum(1 + e for e in edges[lo[r]:lo[r + 1]]) for r in range(world)]
+        if len(edges) >= 4 * world:
+            assert max(cost) <= 1.5 * sum(cost) / world + 4, (edges, world, cost)
+
+
+def test_flag_epochs_grow_monotonically():
+    from geo4d_b200 import sharding
+    a = sharding.reserve_flags(500)
+    b = sharding.reserve_flags(500)
+    c = sharding.reserve_flags(60)
+    assert b >= a + 500 and c >= b + 500
