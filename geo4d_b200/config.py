@@ -11,6 +11,8 @@ TARGET_ALIASES = {
     "lvdm.modules.networks.openaimodel3d.UNetModel": "geo4d_b200.unet.UNetModel",
     "lvdm.models.autoencoder.AutoencoderKL": "geo4d_b200.vae.AutoencoderKL",
     "lvdm.models.samplers.ddim.DDIMSampler": "geo4d_b200.sampler.DDIMSampler",
+    "lvdm.models.samplers.ddim_multiplecond.DDIMSampler": "geo4d_b200.sampler.DDIMSampler_multicond",
+    "lvdm.modules.encoders.resampler.Resampler": "geo4d_b200.resampler.Resampler",
     "dust3r.cloud_opt.optimizer_group.LightPointCloudGroupOptimizer":
         "geo4d_b200.cloud_opt.LightPointCloudGroupOptimizer",
 }

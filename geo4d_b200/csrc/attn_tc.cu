@@ -37,6 +37,7 @@ constexpr int AT_KV_BYTES = 128 * 64 * 2;  // 16 KB per K or V tile
 constexpr int AT_P_BYTES = 128 * 128 * 2;  // 32 KB
 constexpr int AT_SMEM = AT_Q_BYTES + 4 * AT_KV_BYTES + AT_P_BYTES;  // 112 KB
 
+template <bool TWO_SETS>
 __global__ void __launch_bounds__(192, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmK2,
@@ -65,13 +66,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int b = bh / args.H;
   const int bkv = b / args.kv_batch_div;
   const int nkv1 = args.n_kvtiles;
-  const int nkv = nkv1 + args.n_kvtiles2;   // tiles j >= nkv1 belong to the second key/value set
+  const int nkv = TWO_SETS ? nkv1 + args.n_kvtiles2 : nkv1;   // tiles j >= nkv1 belong to the second key/value set
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    if (args.n_kvtiles2) { tma_prefetch_desc(&tmK2); tma_prefetch_desc(&tmV2); }
+    if (TWO_SETS) { tma_prefetch_desc(&tmK2); tma_prefetch_desc(&tmV2); }
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&k_full[s], 1);
@@ -104,7 +105,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int j = 0; j < nkv; ++j) {
         const int st = j & 1;
         const uint32_t ph = (j >> 1) & 1;
-        const bool second = j >= nkv1;
+        const bool second = TWO_SETS && j >= nkv1;
         const int row0 = (second ? j - nkv1 : j) * 128;
         const int bb = second ? b / args.kv_batch_div2 : bkv;
         mbar_wait(&k_empty[st], ph ^ 1);
@@ -147,8 +148,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&v_full[st], ph);
         mbar_wait(p_ready, j & 1);
         tc_fence_after();
-        const uint32_t tOj = j >= nkv1 ? tO + 64 : tO;          // each key/value set has its own accumulator
-        const int jj = j >= nkv1 ? j - nkv1 : j;
+        const uint32_t tOj = (TWO_SETS && j >= nkv1) ? tO + 64 : tO;          // each key/value set has its own accumulator
+        const int jj = (TWO_SETS && j >= nkv1) ? j - nkv1 : j;
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
@@ -167,8 +168,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float sl2 = args.scale_log2;
     float m = -INFINITY, l = 0.f, l_first = 1.f;
     for (int j = 0; j < nkv; ++j) {
-      if (j == nkv1 && j > 0) { l_first = l; m = -INFINITY; l = 0.f; }   // second set: a softmax of its own
-      const bool second = j >= nkv1;
+      if (TWO_SETS && j == nkv1 && j > 0) { l_first = l; m = -INFINITY; l = 0.f; }   // second set: a softmax of its own
+      const bool second = TWO_SETS && j >= nkv1;
       const int jj = second ? j - nkv1 : j;
       const uint32_t tOj = second ? tO + 64 : tO;
       const int kv_valid = min(128, (second ? args.Lk2 : args.Lk) - jj * 128);  // keys of this tile that exist
@@ -246,7 +247,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_wait(pv_done, (nkv - 1) & 1);
     tc_fence_after();
     const int lq = qt * 128 + r;
-    const bool two = args.n_kvtiles2 > 0;
+    constexpr bool two = TWO_SETS;
     const float inv_l = two ? 1.0f / l_first : 1.0f / l;
     const float inv_l2 = 1.0f / l;
     __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(args.out) + ((long long)b * args.Lq + lq) * args.ldo + h * 64;
@@ -344,11 +345,13 @@ static int attention_impl(const void* q, int64_t ldq, const void* k, const void*
   a.Lk2 = two ? Lk2 : 0; a.n_kvtiles2 = two ? (Lk2 + 127) / 128 : 0; a.kv_batch_div2 = two ? kv_batch_div2 : 1;
   a.scale_log2 = scale * 1.4426950408889634f;
   a.out = out; a.ldo = ldo;
-  cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);   // per device, cheap
+  cudaError_t e = two ? cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)
+                      : cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);   // per device, cheap
   if (e != cudaSuccess) { set_last_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return G4_ERR_CUDA; }
   const long long grid = (long long)a.n_qtiles * B * H;
   if (grid > 2147483647ll) { set_last_error("attention: grid too large"); return G4_ERR_UNSUPPORTED; }
-  launch_pdl(attn_fwd_kernel, dim3((int)grid), dim3(192), AT_SMEM, stream, tmQ, tmK, tmV, tmK2, tmV2, a);
+  if (two) launch_pdl(attn_fwd_kernel<true>, dim3((int)grid), dim3(192), AT_SMEM, stream, tmQ, tmK, tmV, tmK2, tmV2, a);
+  else launch_pdl(attn_fwd_kernel<false>, dim3((int)grid), dim3(192), AT_SMEM, stream, tmQ, tmK, tmV, tmK2, tmV2, a);
   return check_launch("attention");
 }
 

@@ -357,6 +357,9 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (args.act == G4_ACT_SILU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) o[j] = silu_f(o[j]);
+          } else if (args.act == G4_ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = gelu_erf_f(o[j]);
           }
           if (rrow) {
             if (res_vec && vec_ok) {
@@ -514,6 +517,7 @@ splitk_reduce_kernel(const ReduceArgs a) {
         float o = fmaf(acc[j], a.alpha, a.bias ? __ldg(a.bias + c0 + j) : 0.f);
         if (rb) o += __ldg(rb + j);
         if (a.act == G4_ACT_SILU) o = silu_f(o);
+        else if (a.act == G4_ACT_GELU) o = gelu_erf_f(o);
         if (rr) o += __bfloat162float(rr[j]);
         acc[j] = o;
       }

@@ -25,7 +25,7 @@ from . import schedule as sched
 from .config import instantiate_from_config
 from .vae import AutoencoderKL, DiagonalGaussianDistribution
 
-_IGNORED_PREFIXES = ("cond_stage_model.", "embedder.", "image_proj_model.", "model_ema.")
+_IGNORED_PREFIXES = ("cond_stage_model.", "embedder.", "model_ema.")   # OpenCLIP towers: outside this port (N3)
 
 
 class DiffusionWrapper(nn.Module):
@@ -99,7 +99,14 @@ class LatentVisualDiffusion(nn.Module):
                                                                                   turning_step)))
         self.cond_stage_model = None
         self.embedder = None
+        # image-token Resampler (ddpm3d.py:2416-2421 `image_proj_model`): native (geo4d_b200/resampler.py); the OpenCLIP
+        # towers that feed it are not part of this port -- their (constant) outputs are handed over, see below
         self.image_proj_model = None
+        if image_proj_stage_config is not None and "target" in image_proj_stage_config:
+            try:
+                self.image_proj_model = instantiate_from_config(image_proj_stage_config)
+            except (ImportError, AttributeError, NotImplementedError):
+                self.image_proj_model = None
         self._cached_cond: Optional[Dict[str, torch.Tensor]] = None
 
     # ------------------------------------------------------------------ checkpoint
@@ -108,6 +115,11 @@ class LatentVisualDiffusion(nn.Module):
         and non-persistent extras are dropped, everything else must match exactly when strict."""
         sd = {k: v for k, v in state_dict.items()
               if not k.startswith(_IGNORED_PREFIXES) and k not in ("logvar", "lvlb_weights")}
+        if self.image_proj_model is None:
+            sd = {k: v for k, v in sd.items() if not k.startswith("image_proj_model.")}
+        elif not any(k.startswith("image_proj_model.") for k in sd):
+            # a state dict without the Resampler (e.g. synthetic weights): keep the module's own tensors
+            sd.update({"image_proj_model." + k: v for k, v in self.image_proj_model.state_dict().items()})
         return super().load_state_dict(sd, strict=strict, **kw)
 
     @property
@@ -120,9 +132,15 @@ class LatentVisualDiffusion(nn.Module):
         return self
 
     # ------------------------------------------------------------------ conditioning
-    def set_cached_conditioning(self, text_emb: torch.Tensor, img_emb: Optional[torch.Tensor] = None):
-        """text_emb [1, 77, 1024] (FrozenOpenCLIPEmbedder output for the fixed prompt) and img_emb
-        [1, 16*t, 1024] (Resampler output for the all-zero image, infer_geo4d.py:150-156)."""
+    def set_cached_conditioning(self, text_emb: torch.Tensor, img_emb: Optional[torch.Tensor] = None,
+                                clip_image_tokens: Optional[torch.Tensor] = None):
+        """text_emb [1, 77, 1024] (FrozenOpenCLIPEmbedder output for the fixed prompt) and either img_emb
+        [1, 16*t, 1024] (Resampler output for the all-zero image, infer_geo4d.py:150-156) or clip_image_tokens
+        [1, 257, 1280] (FrozenOpenCLIPImageEmbedderV2 output), which the native Resampler projects."""
+        if img_emb is None and clip_image_tokens is not None:
+            if self.image_proj_model is None:
+                raise NotImplementedError("no image_proj_model was configured (image_proj_stage_config)")
+            img_emb = self.image_proj_model(clip_image_tokens.to(self.device))
         self._cached_cond = {"text": text_emb, "img": img_emb}
 
     def get_learned_conditioning(self, c):

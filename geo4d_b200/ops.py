@@ -16,7 +16,7 @@ import torch
 from . import _cabi
 from ._cabi import GemmDesc, check, lib
 
-ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
+ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_GELU = 0, 1, 2, 3
 
 TAPS_1 = ((0, 0),)
 TAPS_3x3 = tuple((dx, dy) for dy in (-1, 0, 1) for dx in (-1, 0, 1))  # weight[:, :, ky, kx] order

@@ -64,7 +64,7 @@ void geo4d_debug_gemm_pair_mode(int mode);
  *   - batched matmul (VAE AttnBlock q k^T / p v, ae_modules.py:63-73):             b_batched = 1
  * K (= C) must be a multiple of 64 (pad the channel dim with zeros otherwise).
  * ---------------------------------------------------------------------------------------------- */
-enum { G4_ACT_NONE = 0, G4_ACT_SILU = 1, G4_ACT_GEGLU = 2 };
+enum { G4_ACT_NONE = 0, G4_ACT_SILU = 1, G4_ACT_GEGLU = 2, G4_ACT_GELU = 3 /* exact-erf GELU (nn.GELU()) */ };
 
 typedef struct {
   /* A operand, bf16 */

@@ -176,3 +176,26 @@ def test_native_sqpnp_matches_cv2_sqpnp():
         ok, rv, tv = cv2.solvePnP(world[mask].astype(np.float64), pix[mask], K, None, flags=cv2.SOLVEPNP_SQPNP)
         assert ok and got is not None
         assert np.abs(cv2.Rodrigues(rv)[0] - got[0]).max() < 1e-7 and np.abs(tv.ravel() - got[1]).max() < 1e-7
+
+
+def test_infer_script_has_the_references_flag_surface(golden_dir):
+    """scripts/evaluation/infer_geo4d.py: every option of the reference's get_parser (infer_geo4d.py:688-718, extracted
+    by AST into tests/golden/infer_args_ref.json) exists with the same type / action / default."""
+    import importlib.util
+    import json
+    root = os.path.dirname(os.path.dirname(__file__))
+    spec = importlib.util.spec_from_file_location("infer_geo4d_b200", os.path.join(root, "scripts", "evaluation", "infer_geo4d.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mine = {a.option_strings[0]: a for a in mod.get_parser()._actions if a.option_strings}
+    ref = json.load(open(os.path.join(golden_dir, "infer_args_ref.json")))
+    assert len(ref) >= 25
+    for name, kw in ref.items():
+        assert name in mine, name
+        a = mine[name]
+        if kw.get("action") == "store_true":
+            assert a.nargs == 0 and a.const is True and a.default is False, name
+        else:
+            assert (a.type.__name__ if a.type else "str") == kw.get("type", "str"), name
+            if name != "--config":        # the reference has no default config; this repo ships one
+                assert a.default == kw.get("default"), (name, a.default, kw.get("default"))

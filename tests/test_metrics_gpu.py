@@ -1,0 +1,58 @@
+"""GPU: geo4d_b200.metrics.depth_evaluation on CUDA tensors (the LAD alignment runs as one cooperative
+geo4d_lad_fit launch instead of the reference's torch Adam loop) against the committed outputs of the reference's own
+dust3r.depth_eval.depth_evaluation (tests/golden/metrics_ref.json), and the scene writers of
+LightPointCloudGroupOptimizer (base_opt_group.py:383-464).  Tolerance: 2e-3 relative on every metric (same Adam
+recurrence, fp32, different summation order of the loss / gradient sums)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_depth_evaluation_on_gpu_vs_reference_golden(cuda_device, golden_dir):
+    from geo4d_b200 import metrics
+    from oracle.gen_golden_metrics import cases
+    ref = json.load(open(os.path.join(golden_dir, "metrics_ref.json")))
+    for name, (pred, gt, kw, am) in cases().items():
+        res, err, full, gtf = metrics.depth_evaluation(pred.to(cuda_device), gt.to(cuda_device),
+                                                       align_mask=None if am is None else am.to(cuda_device), **kw)
+        for k, v in ref[name]["metrics"].items():
+            assert abs(res[k] - v) <= 2e-3 * max(1.0, abs(v)), (name, k, res[k], v)
+        assert err.is_cuda and abs(float(err.double().sum()) - ref[name]["err_sum"]) <= 5e-3 * abs(ref[name]["err_sum"]), name
+
+
+def test_scene_writers(cuda_device, tmp_path):
+    """save_tum_poses (wxyz), save_focals / intrinsics, save_depth_maps (npy + colour png + gif),
+    save_conf_maps, save_rgb_imgs -- files exist, shapes and values round-trip."""
+    import cv2
+    from oracle import align as oa
+    from geo4d_b200 import metrics
+    from geo4d_b200.cloud_opt import LightPointCloudGroupOptimizer
+    groups, preds, _ = oa.synthetic_scene(T=16, H=32, W=48, noise=0.003)
+    g = torch.Generator().manual_seed(0)
+    views = [[{"img": torch.rand(3, 32, 48, generator=g) * 2 - 1, "idx": (i,)} for i in gr] for gr in groups]
+    preds_d = [{k: v.to(cuda_device) for k, v in p.items()} for p in preds]
+    scene = LightPointCloudGroupOptimizer(views, preds_d, conf="id", conf_optimize=True, verbose=False, shared_focal=True,
+                                          num_total_iter=12, temporal_smoothing_weight=0.015, translation_weight=1.0,
+                                          depth_traj_start_iter=6, lad_max_iters=100)
+    with torch.enable_grad():
+        scene.compute_global_alignment(init="group", niter=12, schedule="linear", lr=0.03)
+    out = str(tmp_path)
+    scene.save_tum_poses(f"{out}/pred_traj.txt")
+    back = metrics.load_tum_trajectory(f"{out}/pred_traj.txt")
+    tum, ts = scene.get_tum_poses()
+    assert np.allclose(back[0], tum) and np.allclose(back[1], ts)
+    assert np.allclose(metrics.tum_to_matrices(back[0]), scene.get_im_poses().detach().cpu().numpy(), atol=1e-5)
+    scene.save_focals(f"{out}/pred_focal.txt"); scene.save_intrinsics(f"{out}/pred_intrinsics.txt")
+    assert np.loadtxt(f"{out}/pred_focal.txt").shape == (16,) and np.loadtxt(f"{out}/pred_intrinsics.txt").shape == (16, 9)
+    scene.save_depth_maps(out); scene.save_conf_maps(out); scene.save_init_conf_maps(out); scene.save_rgb_imgs(out)
+    d0 = np.load(f"{out}/frame_0000.npy")
+    assert d0.shape == (32, 48) and np.allclose(d0, scene.get_depthmaps()[0].cpu().numpy())
+    assert cv2.imread(f"{out}/frame_colordepth_0003.png").shape == (32, 48, 3)
+    assert os.path.exists(f"{out}/colored_depth_maps.gif") and os.path.exists(f"{out}/conf_5.npy")
+    rgb = cv2.imread(f"{out}/frame_0000.png")[..., ::-1].astype(np.float32) / 255
+    assert np.abs(rgb - scene.imgs[0]).max() < 1.0 / 255 + 1e-6
