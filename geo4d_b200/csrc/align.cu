@@ -638,11 +638,10 @@ extern "C" int geo4d_lad_fit(const float* x, const float* y, int64_t n_per_group
   size_t smem = (size_t)per * 2 * sizeof(float);
   int cache = 1;
   if (smem > 200 * 1024) { smem = 0; cache = 0; }
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr_mask = 0;
+  if (once_per_device(&attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(lad_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) { set_last_error("lad_fit: smem attr: %s", cudaGetErrorString(e)); return G4_ERR_CUDA; }
-    attr = true;
+    if (e != cudaSuccess) { unlatch_device(&attr_mask); set_last_error("lad_fit: smem attr: %s", cudaGetErrorString(e)); return G4_ERR_CUDA; }
   }
   // acc: 3 doubles per window | one arrival ticket per window | one generation word per window (zero on entry)
   unsigned int* ticket = reinterpret_cast<unsigned int*>(acc + 3 * (size_t)G);

@@ -81,6 +81,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& ge
     } else {
       long long t0 = clock64();
       while ((int)(ld_acquire_gpu(&bar[1]) - target) < 0) {
+        __nanosleep(40);   // a waiting CTA shares its SM with a working one (CTA 0's serial section): do not steal issue slots
         if (clock64() - t0 > G4_MBAR_TIMEOUT_CYCLES) {
           printf("g4: align_loop grid barrier timeout (block %d gen %u)\n", (int)blockIdx.x, target);
           __trap();
@@ -315,15 +316,13 @@ align_loop_kernel(const LoopArgs a) {
         const int nl = o / nvmax, i = o % nvmax;
         const float* src = a.part + (long long)nl * a.chunks * PART_STRIDE + i;
         double s = 0.0;
-        int c = 0;
-        for (; c + 8 <= a.chunks; c += 8) {
+        for (int c = 0; c < a.chunks; c += 8) {   // (a partial last batch is predicated, not serialised)
           float v[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __ldcg(src + (long long)(c + j) * PART_STRIDE);
+          for (int j = 0; j < 8; ++j) v[j] = (c + j < a.chunks) ? __ldcg(src + (long long)(c + j) * PART_STRIDE) : 0.f;
 #pragma unroll
           for (int j = 0; j < 8; ++j) s += (double)v[j];
         }
-        for (; c < a.chunks; ++c) s += (double)__ldcg(src + (long long)c * PART_STRIDE);
         img_sum[o] = s;
       }
       __syncthreads();

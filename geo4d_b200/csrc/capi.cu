@@ -77,6 +77,19 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+bool once_per_device(unsigned long long* mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return true; }
+  const unsigned long long bit = 1ull << (dev & 63);
+  const unsigned long long old = __atomic_fetch_or(mask, bit, __ATOMIC_ACQ_REL);
+  return (old & bit) == 0;
+}
+void unlatch_device(unsigned long long* mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return; }
+  __atomic_fetch_and(mask, ~(1ull << (dev & 63)), __ATOMIC_ACQ_REL);
+}
+
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
   PFN_encodeTiled enc = get_encode();

@@ -26,6 +26,11 @@ enum : int {
 
 void set_last_error(const char* fmt, ...);
 int check_launch(const char* what);  // cudaPeekAtLastError -> status
+// Function attributes (dynamic shared memory limits) are per DEVICE: a latch shared by every device / host thread of
+// the process would skip them on the second GPU.  once_per_device(mask) is true the first time it is called with the
+// current device (one bit per ordinal, atomically claimed) -- the re-entrancy rule of include/geo4d_b200.h.
+bool once_per_device(unsigned long long* mask);
+void unlatch_device(unsigned long long* mask);   // the attribute call failed: try again next time
 bool pdl_enabled();                  // programmatic dependent launch (opt-in: GEO4D_PDL=1)
 
 // Encode a tiled bf16 tensor map. dims[0] is the innermost (contiguous) dimension.

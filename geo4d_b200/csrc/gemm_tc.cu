@@ -543,16 +543,16 @@ template <int BLOCK_N, bool TWO>
 static int launch_tap_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                            const GemmArgs& a, int num_sms, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, TWO>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_mask = 0;   // one latch per template instance, one bit per device
+  if (once_per_device(&attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(tap_gemm_kernel<BLOCK_N, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
+      unlatch_device(&attr_mask);
       set_last_error("tap_gemm<%d,%d>: cudaFuncSetAttribute(smem=%d): %s", BLOCK_N, (int)TWO, Cfg::SMEM_BYTES,
                      cudaGetErrorString(e));
       return G4_ERR_CUDA;
     }
-    attr_set = true;
   }
   const int m_tiles = a.tiles_x * a.tiles_y * a.tiles_n;
   int grid;

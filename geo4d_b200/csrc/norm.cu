@@ -447,12 +447,11 @@ extern "C" int geo4d_groupnorm_silu(const void* x, int64_t ldx, void* y, int64_t
   const size_t fold = (size_t)(block.x * block.y / 64) * 64 * sizeof(float);
   if (smem_stats < fold) smem_stats = fold;
   const size_t smem_apply = 2 * (size_t)C * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr_mask = 0;
+  if (once_per_device(&attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    if (e != cudaSuccess) { set_last_error("groupnorm: smem attr: %s", cudaGetErrorString(e)); return G4_ERR_CUDA; }
-    attr = true;
+    if (e != cudaSuccess) { unlatch_device(&attr_mask); set_last_error("groupnorm: smem attr: %s", cudaGetErrorString(e)); return G4_ERR_CUDA; }
   }
   // single cooperative launch when every block can be resident at once (always true for the U-Net shapes)
   if (!g_gn_two_kernels && num_stats <= GN_TICKETS / 4) {
