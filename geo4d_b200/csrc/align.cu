@@ -326,33 +326,50 @@ __global__ void lad_step_kernel(const float* __restrict__ x, const float* __rest
 }
 
 // Whole LAD fit in ONE cooperative launch: every block keeps its slice of (x, y) in shared memory (when it fits)
-// and runs up to `iters` Adam iterations; per iteration the blocks of a window meet at a grid barrier (arrival
-// ticket -> the last block applies the update and bumps the window's generation word, the others poll it).
-// Same arithmetic as lad_step_kernel, ~4 us per iteration instead of one ~20 us launch each.
+// and runs up to `iters` Adam iterations with the current (s, t) in registers.  Per iteration a block reduces its
+// {sum sign(r) x, sum sign(r), sum |r|} in a fixed tree, stores the three sums as its row of `part` and takes a ticket;
+// the LAST block of the window folds the rows in block order (no atomics: the fit is bit-reproducible), applies Adam
+// and PUBLISHES the new (s, t, done) as two 8-byte words that each carry the iteration number -- the other blocks
+// spin on those words only (one L2 round trip from the update to the next iteration, no separate state reads).
+// Same arithmetic and early exit as lad_step_kernel.  Workspace per window (doubles, geo4d_lad_fit_workspace_doubles):
+// [0] {s, iteration} [1] {t, iteration | done << 31} [2] ticket [3 ...] part[blocks][3] floats.
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 __global__ void __launch_bounds__(512, 1)
 lad_fit_kernel(const float* __restrict__ x, const float* __restrict__ y, long long n_per_group,
-               float* __restrict__ state, double* __restrict__ acc, unsigned int* __restrict__ ticket,
-               unsigned int* __restrict__ gen, float lr, float tol, int iters, int cache) {
+               float* __restrict__ state, double* __restrict__ ws, int ws_stride, float lr, float tol, int iters,
+               int cache) {
   extern __shared__ float lsm[];   // [2][slice] x | y when cache != 0
-  __shared__ float s_st[2];
-  __shared__ int s_flag;
+  __shared__ float s_red[16][3];
+  __shared__ float s_st[3];        // s, t, done for the next iteration
+  __shared__ int s_last;
   const int g = blockIdx.y;
-  const long long per = (n_per_group + gridDim.x - 1) / gridDim.x;
+  const int nb = gridDim.x;
+  const long long per = (n_per_group + nb - 1) / nb;
   const long long i0 = (long long)blockIdx.x * per;
   const long long i1 = i0 + per < n_per_group ? i0 + per : n_per_group;
   const int cnt = (int)(i1 > i0 ? i1 - i0 : 0);
   const float* xg = x + (long long)g * n_per_group + i0;
   const float* yg = y + (long long)g * n_per_group + i0;
+  unsigned long long* pub = reinterpret_cast<unsigned long long*>(ws + (size_t)g * ws_stride);
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(pub + 2);
+  float* part = reinterpret_cast<float*>(pub + 3);
+  volatile float* vst = state + g * 9;
   if (cache) {
     for (int i = threadIdx.x; i < cnt; i += blockDim.x) { lsm[i] = xg[i]; lsm[per + i] = yg[i]; }
-    __syncthreads();
   }
-  volatile float* vst = state + g * 9;
+  float sc = vst[0], tc = vst[1];
+  if (vst[8] != 0.f) return;   // already converged (uniform over the blocks of this window)
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int it = 0; it < iters; ++it) {
-    if (threadIdx.x == 0) { s_flag = (vst[8] != 0.f) ? 1 : 0; s_st[0] = vst[0]; s_st[1] = vst[1]; }
-    __syncthreads();
-    if (s_flag) break;   // converged: uniform over the blocks of this window (read after the previous barrier)
-    const float sc = s_st[0], tc = s_st[1];
     float a[3] = {0.f, 0.f, 0.f};
     for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
       const float xv = cache ? lsm[i] : xg[i];
@@ -363,42 +380,72 @@ lad_fit_kernel(const float* __restrict__ x, const float* __restrict__ y, long lo
       a[1] += sgn;
       a[2] += fabsf(r);
     }
-    block_reduce_atomic<3>(a, acc + g * 3);
-    if (threadIdx.x == 0) {
-      __threadfence();
-      const unsigned int tk = atomicAdd(&ticket[g], 1u);
-      if (tk == gridDim.x - 1) {
-        __threadfence();
-        volatile double* va = acc + g * 3;
-        const float gs = (float)va[0], gt = (float)va[1], loss = (float)va[2];
-        float* st = state + g * 9;
-        const float step = st[7] + 1.f;
-        const float bc1 = 1.f - powf(0.9f, step), bc2 = 1.f - powf(0.999f, step);
-        st[2] = 0.9f * st[2] + 0.1f * gs;
-        st[3] = 0.999f * st[3] + 0.001f * gs * gs;
-        st[4] = 0.9f * st[4] + 0.1f * gt;
-        st[5] = 0.999f * st[5] + 0.001f * gt * gt;
-        st[0] -= (lr / bc1) * st[2] / (sqrtf(st[3]) / sqrtf(bc2) + 1e-8f);
-        st[1] -= (lr / bc1) * st[4] / (sqrtf(st[5]) / sqrtf(bc2) + 1e-8f);
-        if (st[7] > 0.f && fabsf(st[6] - loss) < tol) st[8] = 1.f;
-        st[6] = loss;
-        st[7] = step;
-        va[0] = 0.0; va[1] = 0.0; va[2] = 0.0;
-        ticket[g] = 0u;
-        __threadfence();
-        atomicExch(&gen[g], (unsigned int)(it + 1));
-      } else {
-        long long t0 = clock64();
-        while (*reinterpret_cast<volatile unsigned int*>(&gen[g]) < (unsigned int)(it + 1)) {
-          if (clock64() - t0 > G4_MBAR_TIMEOUT_CYCLES) {
-            printf("g4: lad_fit grid barrier timeout (block %d,%d it %d)\n", (int)blockIdx.x, (int)blockIdx.y, it);
-            __trap();
-          }
-        }
-        __threadfence();
-      }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float v = warp_sum(a[k]);
+      if (lane == 0) s_red[warp][k] = v;
     }
     __syncthreads();
+    if (threadIdx.x == 0) {
+      float t3[3] = {0.f, 0.f, 0.f};
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { t3[0] += s_red[w][0]; t3[1] += s_red[w][1]; t3[2] += s_red[w][2]; }
+      __stcg(part + blockIdx.x * 3 + 0, t3[0]); __stcg(part + blockIdx.x * 3 + 1, t3[1]); __stcg(part + blockIdx.x * 3 + 2, t3[2]);
+      __threadfence();
+      s_last = (atomicAdd(ticket, 1u) == (unsigned)nb - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      if (warp == 0) {
+        // fold the rows in a fixed order: lane l takes blocks l, l+32, ... then a shuffle tree
+        double d[3] = {0.0, 0.0, 0.0};
+        for (int b = lane; b < nb; b += 32) {
+          d[0] += (double)__ldcg(part + b * 3 + 0); d[1] += (double)__ldcg(part + b * 3 + 1); d[2] += (double)__ldcg(part + b * 3 + 2);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          d[0] += __shfl_xor_sync(0xffffffffu, d[0], o); d[1] += __shfl_xor_sync(0xffffffffu, d[1], o);
+          d[2] += __shfl_xor_sync(0xffffffffu, d[2], o);
+        }
+        if (lane == 0) {
+          const float gs = (float)d[0], gt = (float)d[1], loss = (float)d[2];
+          const float step = vst[7] + 1.f;
+          const float bc1 = 1.f - powf(0.9f, step), bc2 = 1.f - powf(0.999f, step);
+          const float ms = 0.9f * vst[2] + 0.1f * gs, vs = 0.999f * vst[3] + 0.001f * gs * gs;
+          const float mt = 0.9f * vst[4] + 0.1f * gt, vt = 0.999f * vst[5] + 0.001f * gt * gt;
+          const float sn = vst[0] - (lr / bc1) * ms / (sqrtf(vs) / sqrtf(bc2) + 1e-8f);
+          const float tn = vst[1] - (lr / bc1) * mt / (sqrtf(vt) / sqrtf(bc2) + 1e-8f);
+          const float done = (vst[7] > 0.f && fabsf(vst[6] - loss) < tol) ? 1.f : 0.f;   // |delta loss| < tol: stop after this update
+          vst[2] = ms; vst[3] = vs; vst[4] = mt; vst[5] = vt;
+          vst[0] = sn; vst[1] = tn; vst[6] = loss; vst[7] = step; vst[8] = done;
+          *ticket = 0u;
+          __threadfence();
+          const unsigned int gen = (unsigned)(it + 1);
+          st_volatile_u64(pub + 0, ((unsigned long long)gen << 32) | __float_as_uint(sn));
+          st_volatile_u64(pub + 1, ((unsigned long long)(gen | (done != 0.f ? 0x80000000u : 0u)) << 32) | __float_as_uint(tn));
+          s_st[0] = sn; s_st[1] = tn; s_st[2] = done;
+        }
+      }
+    } else if (threadIdx.x == 0) {
+      const unsigned int gen = (unsigned)(it + 1);
+      unsigned long long w0, w1;
+      long long t0 = clock64();
+      while ((unsigned)((w0 = ld_volatile_u64(pub + 0)) >> 32) != gen ||
+             ((unsigned)((w1 = ld_volatile_u64(pub + 1)) >> 32) & 0x7fffffffu) != gen) {
+        if (clock64() - t0 > G4_MBAR_TIMEOUT_CYCLES) {
+          printf("g4: lad_fit grid barrier timeout (block %d,%d it %d)\n", (int)blockIdx.x, (int)blockIdx.y, it);
+          __trap();
+        }
+      }
+      s_st[0] = __uint_as_float((unsigned)w0);
+      s_st[1] = __uint_as_float((unsigned)w1);
+      s_st[2] = ((unsigned)(w1 >> 32) & 0x80000000u) ? 1.f : 0.f;
+    }
+    __syncthreads();
+    sc = s_st[0]; tc = s_st[1];
+    const bool stop = s_st[2] != 0.f;
+    __syncthreads();   // s_st / s_red / s_last are rewritten next iteration
+    if (stop) break;
   }
 }
 
@@ -625,6 +672,12 @@ extern "C" int geo4d_lad_step(const float* x, const float* y, int64_t n_per_grou
   return check_launch("lad_step");
 }
 
+extern "C" size_t geo4d_lad_fit_workspace_doubles(int G) {
+  const int sms = device_sm_count();
+  const int nb = sms > 0 ? sms : 256;
+  return (size_t)(G < 1 ? 1 : G) * (size_t)(3 + (3 * nb + 1) / 2);
+}
+
 extern "C" int geo4d_lad_fit(const float* x, const float* y, int64_t n_per_group, int G, float* state, double* acc,
                              float lr, float tol, int iters, g4_stream_t stream_) {
   G4_STREAM;
@@ -643,10 +696,9 @@ extern "C" int geo4d_lad_fit(const float* x, const float* y, int64_t n_per_group
     cudaError_t e = cudaFuncSetAttribute(lad_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) { unlatch_device(&attr_mask); set_last_error("lad_fit: smem attr: %s", cudaGetErrorString(e)); return G4_ERR_CUDA; }
   }
-  // acc: 3 doubles per window | one arrival ticket per window | one generation word per window (zero on entry)
-  unsigned int* ticket = reinterpret_cast<unsigned int*>(acc + 3 * (size_t)G);
-  unsigned int* gen = ticket + G;
-  cudaError_t e = cudaMemsetAsync(gen, 0, sizeof(unsigned int) * G, stream);
+  // workspace (geo4d_lad_fit_workspace_doubles(G) doubles): per window {s | it}, {t | it | done}, ticket, part[blocks][3]
+  const int ws_stride = 3 + (3 * sms + 1) / 2;
+  cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(double) * (size_t)G * ws_stride, stream);
   if (e != cudaSuccess) { set_last_error("lad_fit: memset: %s", cudaGetErrorString(e)); return G4_ERR_CUDA; }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(bx, G); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
@@ -654,7 +706,7 @@ extern "C" int geo4d_lad_fit(const float* x, const float* y, int64_t n_per_group
   at[0].id = cudaLaunchAttributeCooperative;
   at[0].val.cooperative = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, lad_fit_kernel, x, y, (long long)n_per_group, state, acc, ticket, gen, lr, tol, iters, cache);
+  e = cudaLaunchKernelEx(&cfg, lad_fit_kernel, x, y, (long long)n_per_group, state, acc, ws_stride, lr, tol, iters, cache);
   if (e != cudaSuccess) { set_last_error("lad_fit: launch: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return G4_ERR_CUDA; }
   return check_launch("lad_fit");
 }

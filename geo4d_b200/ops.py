@@ -474,7 +474,23 @@ def lad_step(x, y, n_per_group: int, G: int, state, acc, lr: float, tol: float =
                                C.c_float(tol), _s()), "geo4d_lad_step")
 
 
+def lad_fit_workspace_size(G: int) -> int:
+    f = lib().geo4d_lad_fit_workspace_doubles
+    f.restype = C.c_size_t
+    return int(f(G))
+
+
+def lad_fit_workspace(G: int, device) -> torch.Tensor:
+    f = lib().geo4d_lad_fit_workspace_doubles
+    f.restype = C.c_size_t
+    return torch.zeros(int(f(G)), device=device, dtype=torch.float64)
+
+
 def lad_fit(x, y, n_per_group: int, G: int, state, acc, lr: float, iters: int, tol: float = 1e-6):
+    """acc: lad_fit_workspace(G, device) (a smaller buffer is replaced: older callers passed 4*G doubles)"""
+    need = lad_fit_workspace_size(G)
+    if acc is None or acc.numel() < need:
+        acc = torch.zeros(need, device=x.device, dtype=torch.float64)
     check(lib().geo4d_lad_fit(_vp(x), _vp(y), C.c_int64(n_per_group), G, _vp(state), _vp(acc), C.c_float(lr),
                               C.c_float(tol), int(iters), _s()), "geo4d_lad_fit")
 

@@ -221,7 +221,10 @@ int geo4d_sqpnp_from_moments(const double* mom, double f, double* R_out, double*
 int geo4d_sqpnp_from_moments_batch(const double* mom, const double* f, int n, double* R_out, double* t_out,
                                    int* ok_out, int threads);
 /* The whole fit (up to `iters` iterations of geo4d_lad_step, same arithmetic and early exit) in one cooperative
- * launch with a per-window grid barrier; needs G <= number of SMs.  acc as above (4*G doubles, zero on entry). */
+ * launch with a per-window grid barrier; needs G <= number of SMs.  acc: geo4d_lad_fit_workspace_doubles(G) doubles of
+ * scratch (per window: the published (s, t) words, an arrival ticket and one row of partial sums per block; the call
+ * clears it).  The per-block sums are folded in block order: the fit is bit-reproducible. */
+size_t geo4d_lad_fit_workspace_doubles(int G);
 int geo4d_lad_fit(const float* x, const float* y, int64_t n_per_group, int G, float* state, double* acc, float lr,
                   float tol, int iters, g4_stream_t stream);
 /* delta<1.25 accuracy of s*x+t vs y under (w>0.5 & x>0.05 & y>0) (depth_eval.py:296-317): out[g] = {ok, n}. */

@@ -199,3 +199,37 @@ def test_infer_script_has_the_references_flag_surface(golden_dir):
             assert (a.type.__name__ if a.type else "str") == kw.get("type", "str"), name
             if name != "--config":        # the reference has no default config; this repo ships one
                 assert a.default == kw.get("default"), (name, a.default, kw.get("default"))
+
+
+def test_minimal_sample_moments_match_the_dense_moment_routine():
+    """init_solvers._minimal_sample_moments (4-point RANSAC hypotheses of the windowed PnP) vs moments_numpy on the
+    same four pixels; a sample with fewer than four valid draws is flagged unusable."""
+    import numpy as np
+    from geo4d_b200 import init_solvers as isv
+    rng = np.random.default_rng(0)
+    H, W = 24, 32
+    pts = rng.standard_normal((H, W, 3)).astype(np.float32)
+    cand = rng.integers(0, H * W, size=(3, 16))
+    conf = (rng.random((3, 16)) > 0.3).astype(np.float32)
+    conf[2, :] = 0.0
+    conf[2, :3] = 1.0                                   # only three valid draws
+    mom, usable = isv._minimal_sample_moments(pts.reshape(-1, 3)[cand], conf, cand, W, W / 2, H / 2)
+    assert list(usable) == [True, True, False]
+    for i in range(2):
+        sel = [int(c) for c, v in zip(cand[i], conf[i] > 0.5) if v][:4]
+        ref = np.zeros(41)
+        for p in sel:
+            mk = np.zeros(H * W, dtype=bool)
+            mk[p] = True
+            ref += isv.moments_numpy(pts, mk.reshape(H, W), W / 2, H / 2)
+        assert np.allclose(mom[i], ref, atol=1e-9)
+    # a minimal sample of an exact pin-hole scene reproduces the camera (SQPnP on 4 points)
+    f = 0.9 * W
+    ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    depth = 2 + 0.5 * np.sin(xs / 5.0) + 0.3 * np.cos(ys / 3.0)
+    cam = np.stack([(xs - W / 2) / f * depth, (ys - H / 2) / f * depth, depth], -1)
+    pix = np.array([[3 * W + 4, 20 * W + 29, 11 * W + 15, 7 * W + 25] + [0] * 12])
+    m4, ok = isv._minimal_sample_moments(cam.reshape(-1, 3)[pix], np.ones((1, 16), dtype=np.float32), pix, W, W / 2, H / 2)
+    sol = isv.sqpnp_from_moments(m4[0], f)
+    assert ok[0] and sol is not None
+    assert np.allclose(sol[0], np.eye(3), atol=1e-6) and np.allclose(sol[1], 0, atol=1e-6)
