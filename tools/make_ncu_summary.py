@@ -22,14 +22,21 @@ if os.path.exists(rep):
     want += [h for h in hdr if "pipe_tensor" in h and h not in want]
     idx = [hdr.index(k) for k in want if k in hdr]
     names = ["attn L2560 self", "attn L640 self", "attn L160 self", "attn cross 77+16 @L2560", "conv3x3 320 @40x64",
-             "conv3x3 640 @20x32", "conv3x3 1280 @5x8 (split-K main)", "split-K reduce", "linear 40960x320->320",
+             "conv3x3 640 @20x32", "conv3x3 1280 @5x8", "split-K reduce", "linear 40960x320->320",
              "GEGLU 320->2560", "GroupNorm+SiLU 16x2560x320", "align loop (3 iterations)"]
     path = os.path.join(REPO, "profiles", "r2_ncu_hot_kernels.csv")
     with open(path, "w") as f:
         f.write("# ncu --set full --clock-control none, one launch per hot kernel (tools/prof_hot.py); cold cache, serialised\n")
         f.write("launch," + ",".join(f"{hdr[i]}[{units[i]}]" if units[i] else hdr[i] for i in idx) + "\n")
+        labels, li = [], 0
+        kcol = hdr.index("Kernel Name")
+        for r in data:   # the split-K reduce row only exists when the library split the 5x8 conv (not with its cost model's BN=64)
+            if li < len(names) and names[li] == "split-K reduce" and "splitk" not in r[kcol]:
+                li += 1
+            labels.append(names[li] if li < len(names) else str(li))
+            li += 1
         for n, r in enumerate(data):
-            f.write((names[n] if n < len(names) else str(n)) + "," + ",".join('"' + r[i][:60] + '"' if hdr[i] == "Kernel Name"
+            f.write(labels[n] + "," + ",".join('"' + r[i][:60] + '"' if hdr[i] == "Kernel Name"
                                                                             else r[i].replace(",", "") for i in idx) + "\n")
     print("wrote", path)
     tcol = [h for h in hdr if h.startswith("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")] or \
