@@ -482,9 +482,8 @@ class LightPointCloudGroupOptimizer(nn.Module):
             ims = torch.tensor([img for _, img in seen], device=dev)
             s, R, T = self._umeyama(pred[i][ks].reshape(-1, 3).contiguous(), pts3d[ims].reshape(-1, 3).contiguous(),
                                     conf[i][ks].reshape(-1).contiguous(), conf_list[ims].reshape(-1).contiguous())
-            sR = torch.tensor(s * R, device=dev, dtype=torch.float32)
-            Tt = torch.tensor(T, device=dev, dtype=torch.float32)
-            new_pts = pred[i] @ sR.T + Tt
+            reg = np.concatenate([s * R, np.asarray(T).reshape(3, 1)], 1).reshape(1, 12)
+            new_pts = ops.transform_points(pred[i].reshape(1, gs * HW, 3), torch.from_numpy(reg)).reshape(gs, HW, 3)
             pts3d[group] = new_pts
             conf_list[group] = conf[i]
             if im_poses[group[0]] is None:
@@ -507,8 +506,8 @@ class LightPointCloudGroupOptimizer(nn.Module):
         s_factor = float(self.get_pw_norm_scale_factor())
         im_poses_np[:, :3, 3] *= s_factor
         pts3d *= s_factor
-        w2c = torch.tensor(np.linalg.inv(im_poses_np), device=dev, dtype=torch.float32)
-        depth = torch.einsum("nj,npj->np", w2c[:, 2, :3], pts3d) + w2c[:, 2, 3:4]
+        w2c = torch.from_numpy(np.linalg.inv(im_poses_np)[:, :3, :].reshape(N, 12))
+        depth = ops.transform_points(pts3d, w2c, depth_only=True)
         sky = conf_list < 1e-4
         sky_distance = depth[0].max()
         depth = torch.where(sky, sky_distance.expand_as(depth), depth)

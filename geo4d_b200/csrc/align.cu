@@ -100,6 +100,29 @@ __global__ void raymap_moments_kernel(const float* __restrict__ raydir, const fl
 }
 
 // ---------------------------------------------------------------------------------------------- K9
+// Affine map of point sets: set i (pts_per_set points) is mapped with its own row-major 3x4 matrix [A | t].
+// mode 0: out[p] = A x[p] + t (3 floats); mode 1: out[p] = third row only (the camera-frame depth of
+// init_from_pts3d_group, init_im_poses.py:612-620).  Replaces the small cuBLAS matmul / einsum of the initialisation.
+__global__ void transform_points_kernel(const float* __restrict__ x, long long pts_per_set, const float* __restrict__ mats,
+                                        float* __restrict__ out, int mode) {
+  const int set = blockIdx.y;
+  float M[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) M[i] = mats[set * 12 + i];
+  const float* xs = x + (long long)set * pts_per_set * 3;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < pts_per_set; p += (long long)gridDim.x * blockDim.x) {
+    const float a = xs[3 * p], b = xs[3 * p + 1], c = xs[3 * p + 2];
+    if (mode == 0) {
+      float* o = out + ((long long)set * pts_per_set + p) * 3;
+      o[0] = M[0] * a + M[1] * b + M[2] * c + M[3];
+      o[1] = M[4] * a + M[5] * b + M[6] * c + M[7];
+      o[2] = M[8] * a + M[9] * b + M[10] * c + M[11];
+    } else {
+      out[(long long)set * pts_per_set + p] = M[8] * a + M[9] * b + M[10] * c + M[11];
+    }
+  }
+}
+
 // Weighted Umeyama moments (what roma.rigid_points_registration reduces; init_im_poses.py:797-800).
 // pass 0: out[0..7)  = {sum w, sum w x(3), sum w y(3)}
 // pass 1: out[0..10) = {sum w |x-xm|^2, sum w (y-ym)(x-xm)^T (9, row-major [i=y][j=x])}  given means[6]
@@ -610,6 +633,21 @@ extern "C" int geo4d_raymap_moments(const float* raydir, const float* raymoment,
   dim3 grid(blocks_for((long long)S * S, 32), T);
   raymap_moments_kernel<<<grid, 256, 0, stream>>>(raydir, raymoment, T, H, W, x0, y0, S, out);
   return check_launch("raymap_moments");
+}
+
+extern "C" int geo4d_transform_points(const float* x, int n_sets, int64_t pts_per_set, const float* mats, float* out,
+                                      int mode, g4_stream_t stream_) {
+  G4_STREAM;
+  if (!x || !mats || !out || n_sets < 1 || n_sets > 65535 || pts_per_set < 1 || (mode != 0 && mode != 1)) {
+    set_last_error("transform_points: bad args"); return G4_ERR_BAD_ARG;
+  }
+  const int sms = device_sm_count(); if (sms <= 0) return G4_ERR_CUDA;
+  int bx = (4 * sms + n_sets - 1) / n_sets;
+  const long long maxbx = (pts_per_set + 255) / 256;
+  if (bx > maxbx) bx = (int)maxbx;
+  if (bx < 1) bx = 1;
+  transform_points_kernel<<<dim3(bx, n_sets), 256, 0, stream>>>(x, pts_per_set, mats, out, mode);
+  return check_launch("transform_points");
 }
 
 extern "C" int geo4d_umeyama_moments(const float* x, const float* y, const float* w1, const float* w2, int64_t n,

@@ -461,6 +461,17 @@ def raymap_moments(raydir: torch.Tensor, raymoment: torch.Tensor, T: int, H: int
     return out
 
 
+def transform_points(x: torch.Tensor, mats: torch.Tensor, depth_only: bool = False) -> torch.Tensor:
+    """x [n_sets, P, 3] fp32 contiguous, mats [n_sets, 12] (row-major 3x4) -> A x + t ([n_sets, P, 3]) or its z row."""
+    assert x.is_contiguous() and x.dtype == torch.float32 and x.dim() == 3 and x.shape[2] == 3
+    n_sets, P = x.shape[0], x.shape[1]
+    m = mats.reshape(n_sets, 12).to(device=x.device, dtype=torch.float32).contiguous()
+    out = torch.empty((n_sets, P) if depth_only else (n_sets, P, 3), device=x.device, dtype=torch.float32)
+    check(lib().geo4d_transform_points(_vp(x), n_sets, C.c_int64(P), _vp(m), _vp(out), 1 if depth_only else 0, _s()),
+          "geo4d_transform_points")
+    return out
+
+
 def umeyama_moments(x: torch.Tensor, y: torch.Tensor, w1: torch.Tensor, w2: Optional[torch.Tensor], npts: int,
                     pass_: int, means: Optional[torch.Tensor]) -> torch.Tensor:
     out = torch.empty(10, device=x.device, dtype=torch.float64)

@@ -37,22 +37,21 @@ def sliding_windows(T: int, stride: int, window: int = 16) -> List[slice]:
 def raymap_to_camera_matrix(raymap: torch.Tensor, crossmap: torch.Tensor) -> torch.Tensor:
     """[1, 3, t, h, w] ray directions / moments -> cam-to-world [t, 4, 4] = [[R, c], [0, 1]]
     (cameras_from_plucker utils/rays.py:387-433 + infer_geo4d.py:657-674).  The per-pixel reductions run in
-    geo4d_raymap_moments; the 3x3 solve / SVD per frame is batched torch.linalg on 16 tiny matrices."""
+    geo4d_raymap_moments; the 3x3 solve / SVD per frame runs on the host in fp64 (16 tiny problems, like the Umeyama
+    registrations of the alignment: no cuSOLVER / cuBLAS call on the path)."""
     _, _, T, H, W = raymap.shape
-    mom = ops.raymap_moments(raymap[0].contiguous(), crossmap[0].contiguous(), T, H, W)  # [T, 18] fp64
-    M = torch.stack([mom[:, 0], mom[:, 1], mom[:, 2], mom[:, 1], mom[:, 3], mom[:, 4], mom[:, 2], mom[:, 4],
-                     mom[:, 5]], -1).reshape(T, 3, 3)
-    b = mom[:, 6:9].unsqueeze(-1)
-    centers = torch.linalg.lstsq(M, b).solution[..., 0]
-    Hm = mom[:, 9:18].reshape(T, 3, 3)
-    U, _, Vh = torch.linalg.svd(Hm, full_matrices=True)
-    sgn = torch.sign(torch.linalg.det(U @ Vh))
-    D = torch.diag_embed(torch.stack([torch.ones_like(sgn), torch.ones_like(sgn), sgn], -1))
-    R = U @ D @ Vh
-    out = torch.eye(4, device=raymap.device, dtype=torch.float64).repeat(T, 1, 1)
-    out[:, :3, :3] = R
-    out[:, :3, 3] = centers
-    return out.float()
+    mom = ops.raymap_moments(raymap[0].contiguous(), crossmap[0].contiguous(), T, H, W).cpu().numpy()  # [T, 18] fp64
+    M = np.stack([mom[:, 0], mom[:, 1], mom[:, 2], mom[:, 1], mom[:, 3], mom[:, 4], mom[:, 2], mom[:, 4], mom[:, 5]],
+                 -1).reshape(T, 3, 3)
+    out = np.tile(np.eye(4), (T, 1, 1))
+    for t in range(T):   # 16 independent 3x3 problems: least-squares line intersection + orthogonal Procrustes, fp64
+        if not np.isfinite(mom[t]).all():
+            continue     # non-finite ray maps: identity pose (LAPACK would raise; the reference would carry NaNs on)
+        out[t, :3, 3] = np.linalg.lstsq(M[t], mom[t, 6:9], rcond=None)[0]
+        U, _, Vh = np.linalg.svd(mom[t, 9:18].reshape(3, 3))
+        sgn = np.sign(np.linalg.det(U @ Vh))
+        out[t, :3, :3] = U @ np.diag([1.0, 1.0, sgn]) @ Vh
+    return torch.from_numpy(out).to(device=raymap.device, dtype=torch.float32)
 
 
 class Geo4DPipeline:

@@ -198,6 +198,11 @@ int geo4d_raymap_moments(const float* raydir, const float* raymoment, int T, int
 /* Weighted Umeyama moments = the reductions of roma.rigid_points_registration(x, y, weights=w1*w2,
  * compute_scaling=True) (init_im_poses.py:797-800).  pass 0: out = {sum w, sum w x(3), sum w y(3)};
  * pass 1 (means = {xm(3), ym(3)}): out = {sum w|x-xm|^2, sum w (y-ym)(x-xm)^T (9)}.  out: 10 doubles. */
+/* Affine map of n_sets point sets [n_sets][pts_per_set][3] with one row-major 3x4 matrix each (mats [n_sets][12]):
+ * mode 0 -> out [n_sets][pts_per_set][3] = A x + t (a window's registration applied to its point maps,
+ * init_im_poses.py:317-330); mode 1 -> out [n_sets][pts_per_set] = third row only (camera-frame depth, :612-620). */
+int geo4d_transform_points(const float* x, int n_sets, int64_t pts_per_set, const float* mats, float* out, int mode,
+                           g4_stream_t stream);
 int geo4d_umeyama_moments(const float* x, const float* y, const float* w1, const float* w2, int64_t n, int pass,
                           const double* means, double* out, g4_stream_t stream);
 /* One fused iteration of the dense part of LightPointCloudGroupOptimizer.forward + backward + Adam on the

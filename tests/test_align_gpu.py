@@ -380,3 +380,18 @@ def test_window_pnp_vs_cv2_ransac_with_structured_outliers(cuda_device, frac):
         assert np.abs(c2w[0, k] - ref[1]).max() < 5e-3, (k, np.abs(c2w[0, k] - ref[1]).max())
         assert abs(focals[0, k] - ref[0]) < 1e-6 * f + 1e-9 or abs(focals[0, k] - ref[0]) / f < 0.04
         prev = focals[0, k]
+
+
+def test_transform_points_kernel(cuda_device):
+    """geo4d_transform_points (a window's registration applied to its point maps / camera-frame depth of the
+    initialisation) vs the matmul / einsum it replaces"""
+    from geo4d_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(5, 1000, 3, generator=g)
+    M = torch.randn(5, 3, 4, generator=g)
+    ref = torch.einsum("sij,spj->spi", M[:, :, :3], x) + M[:, None, :, 3]
+    xd = x.to(cuda_device).contiguous()
+    out = ops.transform_points(xd, M.reshape(5, 12))
+    dep = ops.transform_points(xd, M.reshape(5, 12), depth_only=True)
+    torch.cuda.synchronize()
+    assert torch.allclose(out.cpu(), ref, atol=1e-5) and torch.allclose(dep.cpu(), ref[..., 2], atol=1e-5)
