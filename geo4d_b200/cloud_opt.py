@@ -5,19 +5,22 @@ Same constructor arguments, `compute_global_alignment(init='group', niter, sched
 (`get_depthmaps`, `get_im_poses`, `get_focals`, `get_intrinsics`, `get_pts3d`, `get_tum_poses`, `get_masks`,
 `save_*`) as the reference.  What runs where:
 
-* dense work -- the per-pixel objective, its gradient w.r.t. every log-depth value, the Adam update of
-  the N x HW log-depth maps and the reductions of the gradient w.r.t. poses / focal / window sim(3) /
-  depth scale-shift -- is ONE fused kernel per iteration (geo4d_align_iter); the weighted Umeyama
-  registrations, the LAD scale/shift fit (same Adam iteration as the reference, batched over windows and
-  sync-free) and the delta<1.25 gate are reduction kernels (csrc/align.cu);
-* the O(N + G) small-parameter part (chain rule to the quaternion / signed-log / log-scale parametrisations,
-  temporal-smoothing and trajectory-prior terms, Adam) is a second, single-CTA kernel
-  (geo4d_align_small_step) fed by the matrix-form gradients the dense kernel reduces; an iteration is two
-  kernels + a counter bump, replayed from a CUDA graph.  GEO4D_ALIGN_AUTOGRAD=1 switches that small part to
-  torch autograd + torch.optim.Adam (used by the tests to cross-check the hand-derived gradients);
+* the optimisation loop -- per pixel: objective, gradient w.r.t. every log-depth value, Adam update of the N x HW
+  log-depth maps, reductions of the gradient w.r.t. poses / focal / window sim(3) / depth scale-shift; then the
+  O(N + G) small-parameter part (chain rule to the quaternion / signed-log / log-scale parametrisations,
+  temporal-smoothing and trajectory-prior terms, Adam) -- runs as ONE persistent cooperative kernel per phase
+  (geo4d_align_loop, engine="loop", the default): two grid barriers per iteration, deterministic reductions.  Under
+  torch.distributed the images are split over the ranks and the kernel exchanges the reduced gradients by stores
+  into peer-mapped memory (sharding.PeerExchange), every rank ending with bit-identical parameters.
+  engine="steps" keeps the round-1 form (geo4d_align_iter + geo4d_align_small_step per iteration, CUDA-graph
+  replayed); GEO4D_ALIGN_AUTOGRAD=1 switches the small part to torch autograd + torch.optim.Adam (used by the tests
+  to cross-check the hand-derived gradients);
+* the weighted Umeyama registrations, the LAD scale/shift fit (same Adam iteration as the reference, one cooperative
+  launch per window, sync-free) and the delta<1.25 gate are reduction kernels (csrc/align.cu);
 * the initialisation solvers the reference runs on the CPU -- the shift/focal least-squares fit (scipy LM) and
   the per-frame RANSAC-PnP (cv2, SQPnP) -- reduce their per-pixel sums on the GPU (geo4d_shift_focal_sums,
-  geo4d_pnp_moments) and solve only 1-D / 9x9 problems on the host (init_solvers.py); set
+  geo4d_pnp_moments) and solve only 1-D / 9x9 problems on the host (init_solvers.py, csrc/sqpnp_host.cu): every window
+  in its own frame (windows independent -> batched and shardable), RANSAC hypotheses scored in one launch; set
   GEO4D_INIT_SOLVERS=host to call scipy / cv2 exactly like the reference (1.5-2 s per frame at 320x512).
 """
 from __future__ import annotations
