@@ -79,6 +79,7 @@ def synthetic_sequences(spec, H, W, seed):
         depth = torch.stack([3.0 + 1.5 * torch.sin(xs / W * 3.1 + 0.1 * t) * torch.cos(ys / H * 2.3) for t in range(T)])
         traj = np.zeros((T, 7))
         traj[:, 0] = 0.02 * np.arange(T)
+        traj[:, 1] = 0.01 * np.sin(0.3 * np.arange(T))          # not collinear: the Sim(3) alignment of ATE needs rank >= 2
         traj[:, 2] = 0.01 * np.arange(T)
         traj[:, 3] = 1.0                                        # wxyz identity
         yield {"seq": f"synthetic_{s:02d}", "video": video, "depth": depth, "gt_traj": [traj, np.arange(T).astype(float)]}
