@@ -73,3 +73,45 @@ def test_unet_host_keys_match_reference(golden_dir):
     mine = {k: list(v.shape) for k, v in net.state_dict().items()}
     assert set(mine.keys()) == set(ref.keys())
     assert mine == ref
+
+
+def test_round2_entry_points_validate_arguments_before_touching_cuda(lib):
+    """geo4d_align_loop / geo4d_cross_attention2 / geo4d_transform_points / geo4d_sqpnp_from_moments_batch: bad
+    arguments come back as negative status codes with a message (no CUDA call is made, so this runs without a GPU)."""
+    import numpy as np
+    lib.geo4d_last_error.restype = ctypes.c_char_p
+    assert lib.geo4d_align_loop(None, None) < 0 and b"null" in lib.geo4d_last_error()
+    from geo4d_b200._cabi import AlignLoopDesc
+    d = AlignLoopDesc()                      # all pointers null
+    assert lib.geo4d_align_loop(ctypes.byref(d), None) < 0
+    assert lib.geo4d_transform_points(None, 1, ctypes.c_int64(8), None, None, 0, None) < 0
+    assert b"transform_points" in lib.geo4d_last_error()
+    assert lib.geo4d_cross_attention2(None, ctypes.c_int64(0), None, None, ctypes.c_int64(0), 77, 16, None, None,
+                                      ctypes.c_int64(0), 16, 1, None, ctypes.c_int64(0), 1, 1, 128, ctypes.c_float(0.125), None) < 0
+    lib.geo4d_align_loop_record_doubles.restype = ctypes.c_int
+    assert lib.geo4d_align_loop_record_doubles(11, 8) == 11 * 12 + 8 * 14 + 3
+    lib.geo4d_align_loop_part_floats.restype = ctypes.c_size_t
+    assert lib.geo4d_align_loop_part_floats(16, 18) == 16 * 18 * 128
+    lib.geo4d_lad_fit_workspace_doubles.restype = ctypes.c_size_t
+    assert lib.geo4d_lad_fit_workspace_doubles(3) >= 3 * 4
+    # the host SQPnP batch solver needs no GPU at all: an exact 4-point pin-hole problem per entry
+    f = 100.0
+    pts = np.array([[0.3, -0.2, 3.0], [-0.5, 0.4, 2.5], [0.1, 0.6, 4.0], [0.7, 0.2, 3.5], [-0.2, -0.6, 2.8]])
+    u, v = f * pts[:, 0] / pts[:, 2], f * pts[:, 1] / pts[:, 2]
+    r2 = u * u + v * v
+    mom = np.zeros(41)
+    mom[0:4] = (len(pts), u.sum(), v.sum(), r2.sum())
+    mom[4:7] = pts.sum(0); mom[7:10] = (u[:, None] * pts).sum(0); mom[10:13] = (v[:, None] * pts).sum(0)
+    mom[13:16] = (r2[:, None] * pts).sum(0)
+    mm = np.stack([pts[:, 0] ** 2, pts[:, 0] * pts[:, 1], pts[:, 0] * pts[:, 2], pts[:, 1] ** 2, pts[:, 1] * pts[:, 2], pts[:, 2] ** 2], 1)
+    mom[16:22] = mm.sum(0); mom[22:28] = (u[:, None] * mm).sum(0); mom[28:34] = (v[:, None] * mm).sum(0)
+    mom[34:40] = (r2[:, None] * mm).sum(0); mom[40] = len(pts)
+    B = 5
+    moms = np.ascontiguousarray(np.tile(mom, (B, 1)))
+    fs = np.full(B, f)
+    R, t, ok = np.empty((B, 9)), np.empty((B, 3)), np.zeros(B, dtype=np.int32)
+    lib.geo4d_sqpnp_from_moments_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    assert lib.geo4d_sqpnp_from_moments_batch(moms.ctypes.data, fs.ctypes.data, B, R.ctypes.data, t.ctypes.data,
+                                              ok.ctypes.data, 3) == 1
+    assert ok.all() and np.allclose(R, np.eye(3).reshape(9), atol=1e-7) and np.allclose(t, 0, atol=1e-7)
